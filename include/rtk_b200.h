@@ -1,0 +1,133 @@
+/*
+ * rtk_b200.h - C ABI of the B200 (sm_100a) DPSelect + PivotKV kernels.
+ *
+ * The reference (SCZwangxiao/video-ReTaKe) is pure Python/PyTorch and has no FFI of its own; every entry
+ * point below replaces a span of stock torch ops inside one of its two hot-path operators and is what a
+ * ctypes binding in the reference's own modules would call (INTEGRATION.md shows that binding):
+ *
+ *   retake/visual_compression.py:86-177   memory_bank_compress_keyframe   -> rtk_dpselect_*
+ *   retake/longvideo_cache.py:217-323     PivotKVCache.update             -> rtk_pivot_*
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name ends in _host;
+ *   - bf16 tensors are passed as `const void*` (2-byte elements), indices are int32, positions int64;
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it: no allocation, no
+ *     host synchronisation, no global state; the caller owns every buffer including `workspace`;
+ *   - return value: 0 = ok; >0 = cudaError_t from a launch; <0 = RTK_E_* argument error
+ *     (rtk_error_string() turns either into text).
+ */
+#ifndef RTK_B200_H_
+#define RTK_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTK_ABI_VERSION 1
+
+#define RTK_E_BADARG      (-1)  /* null pointer / non-positive size                         */
+#define RTK_E_ALIGN       (-2)  /* pointer or stride not 16-byte aligned                    */
+#define RTK_E_UNSUPPORTED (-3)  /* shape outside the supported envelope (see each function) */
+#define RTK_E_WORKSPACE   (-4)  /* workspace too small                                      */
+#define RTK_E_DRIVER      (-5)  /* could not obtain cuTensorMapEncodeTiled from the driver  */
+
+int         rtk_version(void);
+const char* rtk_error_string(int code);
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t     rtk_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * DPSelect  (retake/visual_compression.py)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Adjacent-frame cosine distance; replaces visual_compression.py:98-106
+ * (F.cosine_similarity on bf16 + `1 - sim.float()` + the leading row of ones), replaying ATen-CUDA's
+ * bf16 rounding chain and fp32 reduction order bit for bit.
+ *   x    bf16 [T, N, C] contiguous, 16-byte aligned, C % 8 == 0, 256 <= C <= 8160
+ *   halo 0: dis is fp32 [T, N]; row 0 is 1.0, row t is 1 - cos(x[t-1], x[t])
+ *        1: x[0] is the last frame owned by the previous rank; dis is fp32 [T-1, N], row j belongs to x[j+1]
+ */
+int rtk_dpselect_dis(const void* x, int64_t T, int64_t N, int64_t C, int halo, float* dis, void* stream);
+
+/* Peaks + top-t + ascending index list + key-patch mask; replaces visual_compression.py:108-135 (sync=1)
+ * and :141-169,175 (sync=0): max_pool1d_with_indices/unique/nonzero, `+= 2`, topk, sort, mask gather.
+ *   dis    fp32 [T, N]           (T <= 8192)
+ *   t      1 <= t <= T
+ *   idx    int32 [t, N] (sync=0) or [t] (sync=1): kept frame index per output slot, ascending in dim 0
+ *   mask   uint8 [t * N]: 1 where the kept (frame, patch) is a peak (row-major j * N + p)
+ * Ties at the t-th key are resolved like ATen's CUDA radix select: larger keys first, equal keys by
+ * ascending frame index; key order is the radix order (-0 < +0, NaN largest).
+ */
+int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64_t t, int sync,
+                        int32_t* idx, uint8_t* mask, void* stream);
+
+/* Stream compaction of the surviving rows; replaces visual_compression.py:138 / :173.
+ *   out[j, p, :] = x[idx[j, p], p, :] (sync=0)   or   x[idx[j], p, :] (sync=1);  out bf16 [t, N, C]
+ */
+int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t C, const int32_t* idx, int64_t t,
+                        int sync, void* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * PivotKV  (retake/longvideo_cache.py)
+ * ---------------------------------------------------------------------------------------------------- */
+
+/* Reverse rotary embedding of a [heads, L, D] bf16 view; replaces longvideo_cache.py:248-259 with
+ * apply_(multimodal_)rotary_pos_emb(reverse=True) (:75-77 / :108-110) for ONE of q or k.
+ *   x          bf16, element strides (stride_h, stride_l, 1); D even, D % 8 == 0
+ *   cos, sin   bf16 [n_pos, L, D] contiguous as returned by rotary_emb (n_pos = 3 mrope, 1 otherwise)
+ *   mrope_section int32[3] (host) or NULL; channel block i of sections*2 takes position row i % 3
+ *   inv_scale2 = fp32(1 / fp32(attention_scaling ** 2))
+ *   forward    0: out = bf16(bf16(bf16(x*cos) - bf16(rot(x)*sin)) * inv_scale2)     (reverse branch)
+ *              1: out = bf16(bf16(x*cos) + bf16(rot(x)*sin))                        (forward, :79-81)
+ *   out        bf16 [heads, L, D], element strides (out_stride_h, out_stride_l, 1)
+ */
+int rtk_pivot_rope(const void* x, int64_t heads, int64_t L, int64_t D, int64_t stride_h, int64_t stride_l,
+                   const void* cos, const void* sin, int n_pos, const int32_t* mrope_section_host,
+                   float inv_scale2, int forward, void* out, int64_t out_stride_h, int64_t out_stride_l,
+                   void* stream);
+
+/* Bytes of workspace rtk_pivot_score needs for (H, L). */
+size_t rtk_pivot_score_workspace_bytes(int64_t H, int64_t L);
+
+/* Pivot scoring; replaces longvideo_cache.py:260-269: repeat_kv, Q.K^T (tcgen05, bf16 -> fp32 in TMEM),
+ * bf16 rounding, / sqrt(D), fp32 softmax over the chunk-local keys (no mask), bf16 rounding, sum over
+ * queries, bf16 rounding, mean over the G = H / KVH heads of each KV group, bf16 rounding.
+ *   q   bf16 [H, L, D] view, element strides (q_stride_h, q_stride_l, 1), 16-byte aligned, D in {64, 128}
+ *   k   bf16 [KVH, L, D] view, element strides (k_stride_h, k_stride_l, 1)
+ *   head_scores  bf16 [KVH, L]: line-269 value (per-KV-head scores; the all-gather payload when KV heads
+ *                are sharded across GPUs)
+ *   1 <= L <= 16384; H % KVH == 0.
+ */
+int rtk_pivot_score(const void* q, int64_t H, int64_t q_stride_h, int64_t q_stride_l,
+                    const void* k, int64_t KVH, int64_t k_stride_h, int64_t k_stride_l,
+                    int64_t L, int64_t D, void* head_scores, void* workspace, size_t workspace_bytes,
+                    void* stream);
+
+/* Mean over KV heads, key-patch override, top-k, ascending index list; replaces longvideo_cache.py:270-277.
+ *   head_scores bf16 [KVH, L] (all KV heads, i.e. after the all-gather when sharded)
+ *   keymask     uint8 [L] or NULL (keypatches_mask_chunk); masked scores become 1.0
+ *   keep        1 <= keep <= L <= 16384
+ *   keep_idx    int32 [keep] ascending;  score_out bf16 [L] or NULL (line-270 value, before the override)
+ * Tie rule as in rtk_dpselect_select.
+ */
+int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L, const uint8_t* keymask, int64_t keep,
+                     int32_t* keep_idx, void* score_out, void* stream);
+
+/* KV / position compaction; replaces longvideo_cache.py:278-288 and :293-295.
+ *   k, v   bf16 [KVH, L, D] views with element strides (stride_h, stride_l, 1), 16-byte aligned rows
+ *   k_out, v_out bf16 rows [KVH, keep, D] with element strides (out_stride_h, D, 1): k_out[h, j] = k[h, keep_idx[j]]
+ *   pos    int64 [n_pos, L] or NULL;  pos_out int64 [n_pos, keep]
+ *   reforge 1: pos_out[0] = m + trunc(fp32(pos_out[0] - m) * fp32(keep / L)), m = min(pos_out[0])
+ */
+int rtk_pivot_compact(const void* k, const void* v, int64_t KVH, int64_t L, int64_t D,
+                      int64_t stride_h, int64_t stride_l, const int32_t* keep_idx, int64_t keep,
+                      void* k_out, void* v_out, int64_t out_stride_h,
+                      const int64_t* pos, int n_pos, int64_t* pos_out, int reforge, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTK_B200_H_ */

@@ -68,8 +68,11 @@ def aten_cuda_rowsum(xf: torch.Tensor, vec: int = 8, square: bool = False) -> to
     return lane[:, 0]
 
 
-def adjacent_cosine_distance(x: torch.Tensor, reduce: str = "torch", vec: int = 8) -> torch.Tensor:
-    """``dis[T, N]`` fp32 for a memory bank ``x[T, N, C]`` (``visual_compression.py:98-106``)."""
+def adjacent_cosine_distance(x: torch.Tensor, reduce: str = "torch", norm_vec: int = 4, sum_vec: int = 8) -> torch.Tensor:
+    """``dis[T, N]`` fp32 for a memory bank ``x[T, N, C]`` (``visual_compression.py:98-106``).
+
+    ``reduce="aten_cuda"``: ``linalg_vector_norm`` on bf16 reduces with 4-element vectors, ``sum`` on bf16
+    with 8-element vectors (measured on the B200, tests/probes/probe_aten_cuda2.py Q6/Q7)."""
     T, N, C = x.shape
     xf = x.to(torch.float32)
     lowp = x.dtype == BF16
@@ -78,7 +81,7 @@ def adjacent_cosine_distance(x: torch.Tensor, reduce: str = "torch", vec: int = 
     def rowsum(a, square=False):
         flat = a.reshape(-1, C)
         if reduce == "aten_cuda":
-            return aten_cuda_rowsum(flat, vec, square).reshape(a.shape[:-1])
+            return aten_cuda_rowsum(flat, norm_vec if square else sum_vec, square).reshape(a.shape[:-1])
         return (flat * flat if square else flat).sum(-1).reshape(a.shape[:-1])
 
     n = rnd(torch.sqrt(rowsum(xf, square=True)))
@@ -127,12 +130,12 @@ def dpselect_indices(dis: torch.Tensor, t: int, sync: bool, tie: str = "lowest")
 
 def memory_bank_compress_keyframe(memory_bank: torch.Tensor, tgt_mem_len: int, window_size: int = 3,
                                   sync: bool = True, tie: str = "lowest", reduce: str = "torch",
-                                  vec: int = 8, return_indices: bool = False):
+                                  return_indices: bool = False):
     """Oracle twin of the reference operator (same signature plus oracle knobs)."""
     if window_size != 3:
         raise NotImplementedError("the reference only ever calls this with window_size=3")
     B, T, N, C = memory_bank.shape
-    dis = adjacent_cosine_distance(memory_bank[0], reduce=reduce, vec=vec)
+    dis = adjacent_cosine_distance(memory_bank[0], reduce=reduce)
     idx, peaks = dpselect_indices(dis, tgt_mem_len, sync, tie)
     if sync:
         out = memory_bank[:, idx]

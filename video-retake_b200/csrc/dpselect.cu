@@ -1,0 +1,444 @@
+// DPSelect kernels (sm_100a): adjacent-frame cosine distance, peak/top-t selection, row compaction.
+// Replaces the torch op sequence of retake/visual_compression.py:98-177 (memory_bank_compress_keyframe).
+//
+// A1  dpselect_dis_kernel     HBM-bound.  Each warp owns one patch column p over a run of frames and streams
+//     the 2*C-byte rows x[f, p, :] through a private shared-memory ring filled by 1-D TMA bulk copies
+//     (cp.async.bulk + mbarrier), so every row is read from HBM exactly once (plus one halo row per run)
+//     and the loads of the next rows are in flight while the current one is reduced.  The arithmetic replays
+//     ATen-CUDA's F.cosine_similarity on bf16 bit for bit (tests/probes/probe_aten_cuda2.py):
+//       n   = bf16(sqrt(sum_f32 x^2))        reduction order of Reduce.cuh with 4-element vectors
+//       u_i = bf16(x_i / max(n, bf16(1e-8))) (computed as x_i * rcp(n): same bf16 result)
+//       p_i = bf16(u_i * w_i)
+//       sim = bf16(sum_f32 p_i)              reduction order of Reduce.cuh with 8-element vectors
+//       dis = 1 - float(sim)
+//     Both orders are produced from ONE register layout (lane l holds the 4-element vectors l, l+32, ...).
+// A2  dpselect_select_kernel  latency-bound (<= a few MB).  Warp per patch column held in shared memory: peaks,
+//     key = dis + 2*peak, bitwise descent for the t-th largest radix key, ordered emission with ATen's tie rule.
+// A3  dpselect_gather_kernel  HBM-bound row gather (stream compaction of surviving tokens).
+#include "rtk_common.cuh"
+
+namespace rtk {
+
+// ============================================================================================ A1: distance
+constexpr int kDisWarps = 8;
+constexpr int kDisThreads = kDisWarps * kWarp;
+
+struct RowCursor {
+    // iterates the rows one warp has to read: items i = first, first+stride, ...; item -> (run, p);
+    // run r covers computed frames [1 + r*R, min(1 + (r+1)*R, T)) and reads rows [r*R, that end).
+    int item, stride, n_items, N, R, T;
+    int p, f, fbeg, fend;
+    __device__ __forceinline__ void load() {
+        if (item < n_items) {
+            int run = item / N;
+            p = item - run * N;
+            fbeg = run * R;
+            fend = min(1 + (run + 1) * R, T);
+            f = fbeg;
+        }
+    }
+    __device__ __forceinline__ void init(int first, int stride_, int n_items_, int N_, int R_, int T_) {
+        item = first; stride = stride_; n_items = n_items_; N = N_; R = R_; T = T_;
+        load();
+    }
+    __device__ __forceinline__ bool valid() const { return item < n_items; }
+    __device__ __forceinline__ void advance() {
+        if (++f >= fend) { item += stride; load(); }
+    }
+};
+
+template <int K4>
+__global__ void __launch_bounds__(kDisThreads, 1)
+dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis, int T, int N, int C, int R,
+                    int n_items, int stages, int halo) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t row_bytes = (uint32_t)C * 2u;
+    const int nv4 = C >> 2;                                  // 4-element vectors per row
+    uint8_t* ring = smem + (size_t)warp * stages * row_bytes;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t bars = smem_u32(smem + (size_t)kDisWarps * stages * row_bytes) + (uint32_t)(warp * stages) * 8u;
+
+    if (lane == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(bars + 8u * s, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const int gw = blockIdx.x * kDisWarps + warp;
+    const int GW = gridDim.x * kDisWarps;
+    RowCursor cons, prod;
+    cons.init(gw, GW, n_items, N, R, T);
+    prod = cons;
+
+    auto issue = [&](const RowCursor& c, int s) {
+        const __nv_bfloat16* src = x + ((size_t)c.f * N + c.p) * (size_t)C;
+        mbar_arrive_expect_tx(bars + 8u * s, row_bytes);
+        bulk_g2s(ring_u32 + (uint32_t)s * row_bytes, src, row_bytes, bars + 8u * s);
+    };
+    if (lane == 0) {
+        for (int s = 0; s < stages && prod.valid(); ++s) { issue(prod, s); prod.advance(); }
+    }
+
+    const float eps = __uint_as_float(0x322c0000u);          // bf16(1e-8) widened (clamp_min_ on a bf16 tensor)
+    uint2 up[K4];                                            // previous row, normalised, bf16x2 packed
+    int consumed = 0;
+    while (cons.valid()) {
+        const int s = consumed % stages;
+        mbar_wait(bars + 8u * s, (uint32_t)(consumed / stages) & 1u);
+        const uint8_t* row = ring + (size_t)s * row_bytes;
+        uint2 xr[K4];
+#pragma unroll
+        for (int k = 0; k < K4; ++k) {
+            const int v = lane + 32 * k;
+            xr[k] = (v < nv4) ? *reinterpret_cast<const uint2*>(row + 8 * v) : make_uint2(0u, 0u);
+        }
+        // ---- norm: 4 accumulators per lane, sequential over k (ATen Reduce.cuh, input_vec_size 4)
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < K4; ++k) {
+            const float e0 = bf16lo_to_f32(xr[k].x), e1 = bf16hi_to_f32(xr[k].x);
+            const float e2 = bf16lo_to_f32(xr[k].y), e3 = bf16hi_to_f32(xr[k].y);
+            a0 = fmaf(e0, e0, a0); a1 = fmaf(e1, e1, a1); a2 = fmaf(e2, e2, a2); a3 = fmaf(e3, e3, a3);
+        }
+        float ss = ((a0 + a1) + a2) + a3;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ss += __shfl_down_sync(0xffffffffu, ss, off);
+        ss = __shfl_sync(0xffffffffu, ss, 0);
+        // the ring slot is free again (all lanes hold their copy in registers): refill it
+        __syncwarp();
+        if (lane == 0 && prod.valid()) { issue(prod, s); prod.advance(); }
+
+        float nrm = round_bf16(__fsqrt_rn(ss));
+        nrm = fmaxf(nrm, eps);
+        const float rcp = __frcp_rn(nrm);
+#pragma unroll
+        for (int k = 0; k < K4; ++k) {
+            xr[k].x = pack_bf16x2_rn(bf16lo_to_f32(xr[k].x) * rcp, bf16hi_to_f32(xr[k].x) * rcp);
+            xr[k].y = pack_bf16x2_rn(bf16lo_to_f32(xr[k].y) * rcp, bf16hi_to_f32(xr[k].y) * rcp);
+        }
+        if (cons.f != cons.fbeg) {
+            // ---- sum of rounded products in the 8-element-vector order (Reduce.cuh, input_vec_size 8):
+            // 8-vector l'+32k' = 4-vectors (2l'+h)+64k'; for l'<16 they sit in lanes 2l'+h at even k,
+            // for l'>=16 in lanes 2(l'-16)+h at odd k.
+            float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < K4; ++k) {
+                const uint32_t p01 = mul_bf16x2_rn(up[k].x, xr[k].x);
+                const uint32_t p23 = mul_bf16x2_rn(up[k].y, xr[k].y);
+                if ((k & 1) == 0) {
+                    e0 += bf16lo_to_f32(p01); e1 += bf16hi_to_f32(p01);
+                    e2 += bf16lo_to_f32(p23); e3 += bf16hi_to_f32(p23);
+                } else {
+                    o0 += bf16lo_to_f32(p01); o1 += bf16hi_to_f32(p01);
+                    o2 += bf16lo_to_f32(p23); o3 += bf16hi_to_f32(p23);
+                }
+            }
+            const float se = ((e0 + e1) + e2) + e3;          // accumulators 0..3 of 8-lane l' (even lanes)
+            const float so = ((o0 + o1) + o2) + o3;
+            const float te = __shfl_up_sync(0xffffffffu, se, 1);
+            const float to = __shfl_up_sync(0xffffffffu, so, 1);
+            const float ve = (((te + e0) + e1) + e2) + e3;   // odd lanes: full 8-accumulator fold
+            const float vo = (((to + o0) + o1) + o2) + o3;
+            float v = ve + vo;                               // shfl-down offset 16 in 8-lane space
+            v += __shfl_down_sync(0xffffffffu, v, 16);       // offset 8
+            v += __shfl_down_sync(0xffffffffu, v, 8);        // offset 4
+            v += __shfl_down_sync(0xffffffffu, v, 4);        // offset 2
+            v += __shfl_down_sync(0xffffffffu, v, 2);        // offset 1  -> 8-lane 0 == physical lane 1
+            if (lane == 1) dis[(size_t)(cons.f - halo) * N + cons.p] = 1.0f - round_bf16(v);
+        } else if (cons.f == 0 && !halo) {
+            if (lane == 0) dis[cons.p] = 1.0f;
+        }
+#pragma unroll
+        for (int k = 0; k < K4; ++k) up[k] = xr[k];
+        ++consumed;
+        cons.advance();
+    }
+}
+
+__global__ void fill_f32_kernel(float* p, int n, float v) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+template <int K4>
+static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, cudaStream_t st) {
+    int dev = 0, sms = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    const size_t row_bytes = (size_t)C * 2;
+    int stages = (int)(((size_t)smem_max - 1024) / (kDisWarps * row_bytes));
+    if (stages > 8) stages = 8;
+    if (stages < 2) return RTK_E_UNSUPPORTED;
+    const size_t smem = (size_t)kDisWarps * stages * row_bytes + (size_t)kDisWarps * stages * 8;
+    // run length: long enough that the halo re-read is small, short enough to give every warp >= 4 items
+    const long long frames = T - 1;
+    const long long warps = (long long)sms * kDisWarps;
+    long long R = (frames * N) / (warps * 4);
+    if (R > 32) R = 32;
+    if (R < 4) R = 4;
+    if (R > frames) R = frames;
+    const long long runs = (frames + R - 1) / R;
+    const long long n_items = runs * N;
+    long long grid = (n_items + kDisWarps - 1) / kDisWarps;
+    if (grid > sms) grid = sms;
+    auto kern = dpselect_dis_kernel<K4>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    kern<<<(unsigned)grid, kDisThreads, smem, st>>>((const __nv_bfloat16*)x, dis, T, N, C, (int)R, (int)n_items,
+                                                     stages, halo);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+// ============================================================================================== A2: select
+constexpr int kSelWarps = 8;
+
+// one warp: indices of the t largest keys of `keys[0..T)` (radix-ordered uint32) in ascending index order;
+// ties at the threshold go to the lowest indices (ATen sbtopk/mbtopk gather order).
+template <typename Emit>
+__device__ __forceinline__ void warp_select_top(const uint32_t* keys, int T, int t, int lane, Emit emit) {
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
+        int cnt = 0;
+        for (int i = lane; i < T; i += 32) cnt += (keys[i] >= cand);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (cnt >= t) prefix = cand;
+    }
+    int gt = 0;
+    for (int i = lane; i < T; i += 32) gt += (keys[i] > prefix);
+    gt = __reduce_add_sync(0xffffffffu, gt);
+    const int need = t - gt;                                  // equal keys to take, lowest index first
+    int kept = 0, eqs = 0;
+    const uint32_t lt = (1u << lane) - 1u;
+    for (int base = 0; base < T; base += 32) {
+        const int i = base + lane;
+        const uint32_t key = (i < T) ? keys[i] : 0u;
+        const bool is_eq = (i < T) && key == prefix;
+        const uint32_t beq = __ballot_sync(0xffffffffu, is_eq);
+        const bool keep = (i < T) && (key > prefix || (is_eq && eqs + __popc(beq & lt) < need));
+        const uint32_t bk = __ballot_sync(0xffffffffu, keep);
+        if (keep) emit(kept + __popc(bk & lt), i);
+        kept += __popc(bk);
+        eqs += __popc(beq);
+    }
+}
+
+__device__ __forceinline__ bool is_peak(const float* d, int i, int T) {
+    // max_pool1d_with_indices(window 3, pad 1) keeps the first maximum: strict on the left, >= on the right
+    const float c = d[i];
+    const bool l = (i == 0) || (c > d[i - 1]) || (c != c && d[i - 1] == d[i - 1]);
+    const bool r = (i == T - 1) || (c >= d[i + 1]) || (c != c);
+    return l && r;
+}
+
+// sync == 0: CTA handles 8 consecutive patch columns, one warp each.
+__global__ void __launch_bounds__(kSelWarps * kWarp)
+dpselect_select_patch_kernel(const float* __restrict__ dis, int T, int N, int t, int32_t* __restrict__ idx,
+                             uint8_t* __restrict__ mask) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* sd = reinterpret_cast<float*>(smem);               // [8][T] raw distances, then radix keys in place
+    uint8_t* spk = smem + (size_t)kSelWarps * T * 4;          // [8][T] peak flags
+    const int p0 = blockIdx.x * kSelWarps;
+    const int np = min(kSelWarps, N - p0);
+    for (int i = threadIdx.x; i < T * kSelWarps; i += blockDim.x) {
+        const int tt = i / kSelWarps, j = i - tt * kSelWarps;
+        if (j < np) sd[j * T + tt] = dis[(size_t)tt * N + p0 + j];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp >= np) return;
+    float* d = sd + warp * T;
+    uint8_t* pk = spk + warp * T;
+    for (int i = lane; i < T; i += 32) pk[i] = is_peak(d, i, T);
+    __syncwarp();
+    uint32_t* keys = reinterpret_cast<uint32_t*>(d);
+    for (int i = lane; i < T; i += 32) {
+        const float v = pk[i] ? d[i] + 2.0f : d[i];
+        keys[i] = f32_to_ordered(v);
+    }
+    __syncwarp();
+    const int p = p0 + warp;
+    warp_select_top(keys, T, t, lane, [&](int slot, int i) {
+        idx[(size_t)slot * N + p] = i;
+        mask[(size_t)slot * N + p] = pk[i];
+    });
+}
+
+// fp32 sum of one contiguous row in the order ATen's CUDA reduce kernel uses for `dis.mean(1)` (Reduce.cuh):
+//  n >= 128: "vectorize along input" - an unaligned head (lanes shift..3 take one element each), then lane l owns
+//            the aligned float4 vectors l, l+32, ... with one accumulator per vector element, then a scalar tail
+//            folded into accumulator 0;
+//  n <  128: block width bw = min(last_pow2(n), 32); lane l owns elements l, l+bw, ... dealt round-robin to four
+//            accumulators;
+// accumulators are folded ((a0+a1)+a2)+a3 and lanes with a shfl-down tree.  Result valid in lane 0.
+__device__ __forceinline__ float aten_row_sum_f32(const float* __restrict__ row, int n, int lane) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int width = 32;
+    if (n >= 128) {
+        const float* data = row;
+        int end = n;
+        const int shift = (int)(((uintptr_t)row & 15u) >> 2);
+        if (shift > 0) {
+            data -= shift;
+            end += shift;
+            if (lane >= shift && lane < 4) a0 = a0 + data[lane];
+            end -= 4;
+            data += 4;
+        }
+        for (int idx = lane; idx * 4 + 3 < end; idx += 32) {
+            const float4 q = *reinterpret_cast<const float4*>(data + 4 * idx);
+            a0 += q.x; a1 += q.y; a2 += q.z; a3 += q.w;
+        }
+        const int tail = end - end % 4 + lane;
+        if (tail < end) a0 += data[tail];
+    } else {
+        width = 1;
+        while (width * 2 <= n && width < 32) width *= 2;
+        if (lane < width) {
+            int idx = lane;
+            while (idx + 3 * width < n) {
+                a0 += row[idx]; a1 += row[idx + width]; a2 += row[idx + 2 * width]; a3 += row[idx + 3 * width];
+                idx += 4 * width;
+            }
+            if (idx < n) { a0 += row[idx]; idx += width; }
+            if (idx < n) { a1 += row[idx]; idx += width; }
+            if (idx < n) { a2 += row[idx]; idx += width; }
+            if (idx < n) { a3 += row[idx]; }
+        }
+    }
+    float s = ((a0 + a1) + a2) + a3;
+    for (int off = width >> 1; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    return s;
+}
+
+// sync == 1: per-frame mean over patches (ATen mean: fp32 sum in Reduce.cuh order with 4-element vectors,
+// times fp32(1/N)), then one warp selects frames; the mask row of each kept frame is replicated N times.
+__global__ void __launch_bounds__(kSelWarps * kWarp)
+dpselect_select_sync_kernel(const float* __restrict__ dis, int T, int N, int t, int32_t* __restrict__ idx,
+                            uint8_t* __restrict__ mask) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* d = reinterpret_cast<float*>(smem);                // [T]
+    uint8_t* pk = smem + (size_t)T * 4;                       // [T]
+    int32_t* sel = reinterpret_cast<int32_t*>(smem + (size_t)T * 4 + (((size_t)T + 15) & ~(size_t)15));  // [t]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float rcpN = 1.0f / (float)N;
+    for (int tt = warp; tt < T; tt += kSelWarps) {
+        const float s = aten_row_sum_f32(dis + (size_t)tt * N, N, lane);
+        if (lane == 0) d[tt] = s * rcpN;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += blockDim.x) pk[i] = is_peak(d, i, T);
+    __syncthreads();
+    uint32_t* keys = reinterpret_cast<uint32_t*>(d);
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const float v = pk[i] ? d[i] + 2.0f : d[i];
+        keys[i] = f32_to_ordered(v);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        warp_select_top(keys, T, t, lane, [&](int slot, int i) {
+            sel[slot] = i;
+            idx[slot] = i;
+        });
+    }
+    __syncthreads();
+    for (size_t i = threadIdx.x; i < (size_t)t * N; i += blockDim.x) mask[i] = pk[sel[i / N]];
+}
+
+// ============================================================================================== A3: gather
+// out[j, p, :] = x[idx[...], p, :]; one warp per output row, 16-byte vectors, 8 loads in flight per lane.
+__global__ void __launch_bounds__(256)
+dpselect_gather_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ idx, uint4* __restrict__ out,
+                       int N, int nvec, long long rows, int sync) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long GW = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = gw; r < rows; r += GW) {
+        const long long j = r / N;
+        const int p = (int)(r - j * N);
+        const int src_t = sync ? idx[j] : idx[r];
+        const uint4* src = x + ((size_t)src_t * N + p) * (size_t)nvec;
+        uint4* dst = out + (size_t)r * nvec;
+        int v = lane;
+        for (; v + 7 * 32 < nvec; v += 8 * 32) {
+            uint4 b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) b[u] = __ldg(src + v + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dst[v + 32 * u] = b[u];
+        }
+        for (; v < nvec; v += 32) dst[v] = __ldg(src + v);
+    }
+}
+
+}  // namespace rtk
+
+// =================================================================================================== C ABI
+using namespace rtk;
+
+extern "C" int rtk_dpselect_dis(const void* x, int64_t T, int64_t N, int64_t C, int halo, float* dis, void* stream) {
+    if (!x || !dis || T < 1 || N < 1) return RTK_E_BADARG;
+    if (C % 8 != 0 || C < 256 || C > 8160) return RTK_E_UNSUPPORTED;
+    if (((uintptr_t)x & 15u) != 0) return RTK_E_ALIGN;
+    if (T > (1 << 20) || N > (1 << 20) || T * N > (1ll << 31) - 1) return RTK_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T == 1) {
+        if (halo) return 0;
+        fill_f32_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(dis, (int)N, 1.0f);
+        RTK_CHECK_LAUNCH();
+        return 0;
+    }
+    const int k4 = (int)((C / 4 + 31) / 32);
+    if (k4 <= 2) return launch_dis<2>(x, (int)T, (int)N, (int)C, halo, dis, st);
+    if (k4 <= 4) return launch_dis<4>(x, (int)T, (int)N, (int)C, halo, dis, st);
+    if (k4 <= 9) return launch_dis<9>(x, (int)T, (int)N, (int)C, halo, dis, st);
+    if (k4 <= 16) return launch_dis<16>(x, (int)T, (int)N, (int)C, halo, dis, st);
+    if (k4 <= 28) return launch_dis<28>(x, (int)T, (int)N, (int)C, halo, dis, st);
+    if (k4 <= 32) return launch_dis<32>(x, (int)T, (int)N, (int)C, halo, dis, st);
+    if (k4 <= 48) return launch_dis<48>(x, (int)T, (int)N, (int)C, halo, dis, st);
+    return launch_dis<64>(x, (int)T, (int)N, (int)C, halo, dis, st);
+}
+
+extern "C" int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64_t t, int sync, int32_t* idx,
+                                   uint8_t* mask, void* stream) {
+    if (!dis || !idx || !mask || T < 1 || N < 1 || t < 1 || t > T) return RTK_E_BADARG;
+    if (T > 8192) return RTK_E_UNSUPPORTED;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (sync) {
+        if (((uintptr_t)dis & 3u) != 0) return RTK_E_ALIGN;
+        const size_t smem = (size_t)T * 4 + (((size_t)T + 15) & ~(size_t)15) + (size_t)t * 4;
+        cudaError_t e = cudaFuncSetAttribute(dpselect_select_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        dpselect_select_sync_kernel<<<1, kSelWarps * kWarp, smem, st>>>(dis, (int)T, (int)N, (int)t, idx, mask);
+    } else {
+        const size_t smem = (size_t)kSelWarps * T * 5;
+        cudaError_t e = cudaFuncSetAttribute(dpselect_select_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        const unsigned grid = (unsigned)((N + kSelWarps - 1) / kSelWarps);
+        dpselect_select_patch_kernel<<<grid, kSelWarps * kWarp, smem, st>>>(dis, (int)T, (int)N, (int)t, idx, mask);
+    }
+    RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t C, const int32_t* idx, int64_t t,
+                                   int sync, void* out, void* stream) {
+    if (!x || !idx || !out || T < 1 || N < 1 || C < 1 || t < 1) return RTK_E_BADARG;
+    if (C % 8 != 0) return RTK_E_UNSUPPORTED;
+    if ((((uintptr_t)x | (uintptr_t)out) & 15u) != 0) return RTK_E_ALIGN;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long rows = (long long)t * N;
+    long long grid = (rows + 7) / 8;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    dpselect_gather_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, idx, (uint4*)out, (int)N, (int)(C / 8), rows, sync);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}

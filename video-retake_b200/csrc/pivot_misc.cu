@@ -1,0 +1,293 @@
+// PivotKV side kernels (sm_100a): rotary (un)rotation, KV-head mean + top-k selection, KV / position compaction.
+// Replaces retake/longvideo_cache.py:248-259 (B0), :270-277 (B2), :278-306 (B3).
+#include <climits>
+
+#include "rtk_common.cuh"
+
+namespace rtk {
+
+// ======================================================================================== B0: rotary
+struct RopeParams {
+    int heads, L, D, n_pos, forward;
+    long long stride_h, stride_l, out_stride_h, out_stride_l;
+    int bound[6];            // exclusive channel boundaries of the six mrope blocks (sections * 2)
+    float inv_scale2;
+};
+
+__device__ __forceinline__ int rope_pos_row(const RopeParams& p, int c) {
+    if (p.n_pos == 1) return 0;
+    int i = 0;
+    while (i < 5 && c >= p.bound[i]) ++i;
+    return i % 3;
+}
+
+// one thread: 8 channels of the lower half and the 8 partner channels of the upper half of one (head, token)
+__global__ void __launch_bounds__(256)
+pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ cos_t,
+                  const __nv_bfloat16* __restrict__ sin_t, __nv_bfloat16* __restrict__ out, RopeParams p) {
+    const int half = p.D >> 1;
+    const int vec_per_row = half >> 3;
+    const long long total = (long long)p.heads * p.L * vec_per_row;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vec_per_row);
+        const long long hl = i / vec_per_row;
+        const int l = (int)(hl % p.L);
+        const int h = (int)(hl / p.L);
+        const int c0 = v * 8;
+        const __nv_bfloat16* src = x + h * p.stride_h + l * p.stride_l;
+        __nv_bfloat16* dst = out + h * p.out_stride_h + l * p.out_stride_l;
+        uint4 lo4 = *reinterpret_cast<const uint4*>(src + c0);
+        uint4 hi4 = *reinterpret_cast<const uint4*>(src + c0 + half);
+        const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(&lo4);
+        const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(&hi4);
+        uint4 ol4, oh4;
+        __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(&ol4);
+        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&oh4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int ca = c0 + e, cb = c0 + e + half;
+            const size_t ia = ((size_t)rope_pos_row(p, ca) * p.L + l) * p.D + ca;
+            const size_t ib = ((size_t)rope_pos_row(p, cb) * p.L + l) * p.D + cb;
+            const float xa = __bfloat162float(xl[e]), xb = __bfloat162float(xh[e]);
+            const float cosa = __bfloat162float(cos_t[ia]), sina = __bfloat162float(sin_t[ia]);
+            const float cosb = __bfloat162float(cos_t[ib]), sinb = __bfloat162float(sin_t[ib]);
+            // rotate_half: lower half pairs with -x[c + D/2], upper half with +x[c - D/2]
+            const float ta = round_bf16(xa * cosa), ra = round_bf16(-xb * sina);
+            const float tb = round_bf16(xb * cosb), rb = round_bf16(xa * sinb);
+            float ya, yb;
+            if (p.forward) {
+                ya = ta + ra;
+                yb = tb + rb;
+            } else {
+                ya = round_bf16(ta - ra) * p.inv_scale2;
+                yb = round_bf16(tb - rb) * p.inv_scale2;
+            }
+            ol[e] = __float2bfloat16_rn(ya);
+            oh[e] = __float2bfloat16_rn(yb);
+        }
+        *reinterpret_cast<uint4*>(dst + c0) = ol4;
+        *reinterpret_cast<uint4*>(dst + c0 + half) = oh4;
+    }
+}
+
+// ======================================================================================== B2: select
+constexpr int kSelThreads = 1024;
+
+// block-wide: ascending indices of the `keep` largest radix keys in keys[0..L); ties -> lowest index.
+__device__ void block_select_top(const uint32_t* keys, int L, int keep, int32_t* out_idx, int* sh /* >= 40 ints */) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (L + kSelThreads - 1) / kSelThreads;
+    const int beg = min(tid * per, L), end = min(beg + per, L);
+    uint32_t prefix = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+        const uint32_t cand = prefix | (1u << bit);
+        int cnt = 0;
+        for (int i = beg; i < end; ++i) cnt += (keys[i] >= cand);
+        cnt = __reduce_add_sync(0xffffffffu, cnt);
+        if (tid == 0) sh[0] = 0;
+        __syncthreads();
+        if (lane == 0 && cnt) atomicAdd(&sh[0], cnt);
+        __syncthreads();
+        if (sh[0] >= keep) prefix = cand;
+        __syncthreads();
+    }
+    // per-thread counts of greater / equal keys, block exclusive scans
+    int gt = 0, eq = 0;
+    for (int i = beg; i < end; ++i) { gt += (keys[i] > prefix); eq += (keys[i] == prefix); }
+    auto block_excl_scan = [&](int v, int& total) {
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += n;
+        }
+        __syncthreads();
+        if (lane == 31) sh[1 + warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int w = sh[1 + lane], winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int n = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += n;
+            }
+            sh[1 + lane] = winc - w;
+            if (lane == 31) sh[33] = winc;
+        }
+        __syncthreads();
+        total = sh[33];
+        return sh[1 + warp] + inc - v;
+    };
+    int gt_total, eq_total;
+    const int gt_before = block_excl_scan(gt, gt_total);
+    const int eq_before = block_excl_scan(eq, eq_total);
+    const int need = keep - gt_total;                          // equal keys to take, lowest index first
+    const int eq_taken_before = min(eq_before, need);
+    int slot = gt_before + eq_taken_before;
+    int eq_seen = eq_before;
+    for (int i = beg; i < end; ++i) {
+        const uint32_t k = keys[i];
+        bool take = k > prefix;
+        if (k == prefix) { take = eq_seen < need; ++eq_seen; }
+        if (take) out_idx[slot++] = i;
+    }
+}
+
+__global__ void __launch_bounds__(kSelThreads)
+pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int L, const uint8_t* __restrict__ keymask,
+                    int keep, int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ score_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint32_t* keys = reinterpret_cast<uint32_t*>(smem);        // [L]
+    int* sh = reinterpret_cast<int*>(smem + (size_t)L * 4);    // scratch
+    const float rcp = 1.0f / (float)KVH;
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        // ATen mean(0): 4 accumulators over the reduced dim, folded ((v0+v1)+v2)+v3, times fp32(1/KVH)
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < KVH; ++j) v[j & 3] += __bfloat162float(head_scores[(size_t)j * L + i]);
+        const __nv_bfloat16 s = __float2bfloat16_rn((((v[0] + v[1]) + v[2]) + v[3]) * rcp);
+        if (score_out) score_out[i] = s;
+        const float f = (keymask && keymask[i]) ? 1.0f : __bfloat162float(s);
+        keys[i] = f32_to_ordered(f);
+    }
+    __syncthreads();
+    block_select_top(keys, L, keep, keep_idx, sh);
+}
+
+// ======================================================================================= B3: compaction
+// grid.x blocks gather KV rows (one 16-byte vector per thread-iteration); the LAST block handles positions.
+struct CompactParams {
+    int KVH, L, D, keep, n_pos, reforge;
+    long long stride_h, stride_l, out_stride_h;
+    float ratio;              // fp32(keep / L)
+};
+
+__global__ void __launch_bounds__(256)
+pivot_compact_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                     const int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ k_out,
+                     __nv_bfloat16* __restrict__ v_out, const long long* __restrict__ pos,
+                     long long* __restrict__ pos_out, CompactParams p) {
+    if (blockIdx.x == gridDim.x - 1) {
+        if (!pos) return;
+        __shared__ long long smin[32];
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        for (int r = p.reforge ? 1 : 0; r < p.n_pos; ++r)
+            for (int j = tid; j < p.keep; j += blockDim.x) pos_out[(size_t)r * p.keep + j] = pos[(size_t)r * p.L + keep_idx[j]];
+        if (!p.reforge) return;
+        long long mn = LLONG_MAX;
+        for (int j = tid; j < p.keep; j += blockDim.x) mn = min(mn, pos[keep_idx[j]]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if (lane == 0) smin[warp] = mn;
+        __syncthreads();
+        mn = smin[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mn = min(mn, smin[w]);
+        // m + ((p - m) * ratio).long(): int64 tensor times python float -> fp32 product, truncation toward zero
+        for (int j = tid; j < p.keep; j += blockDim.x) {
+            const float d = (float)(pos[keep_idx[j]] - mn);
+            pos_out[j] = mn + (long long)(d * p.ratio);
+        }
+        return;
+    }
+    const int vec_per_row = p.D >> 3;
+    const long long total = (long long)p.KVH * p.keep * vec_per_row;
+    const long long nthreads = (long long)(gridDim.x - 1) * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+        const int c = (int)(i % vec_per_row);
+        const long long hj = i / vec_per_row;
+        const int j = (int)(hj % p.keep);
+        const int h = (int)(hj / p.keep);
+        const size_t so = (size_t)h * p.stride_h + (size_t)keep_idx[j] * p.stride_l + (size_t)c * 8;
+        const size_t dof = (size_t)h * p.out_stride_h + (size_t)j * p.D + (size_t)c * 8;
+        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(k + so));
+        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(v + so));
+        *reinterpret_cast<uint4*>(k_out + dof) = kv;
+        *reinterpret_cast<uint4*>(v_out + dof) = vv;
+    }
+}
+
+long long g_launches = 0;
+
+}  // namespace rtk
+
+using namespace rtk;
+
+extern "C" int rtk_version(void) { return RTK_ABI_VERSION; }
+
+extern "C" int64_t rtk_launch_count(void) { return (int64_t)rtk::g_launches; }
+
+extern "C" const char* rtk_error_string(int code) {
+    if (code == 0) return "ok";
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    switch (code) {
+        case RTK_E_BADARG: return "rtk: bad argument (null pointer or non-positive size)";
+        case RTK_E_ALIGN: return "rtk: pointer or stride not 16-byte aligned";
+        case RTK_E_UNSUPPORTED: return "rtk: shape outside the supported envelope";
+        case RTK_E_WORKSPACE: return "rtk: workspace too small";
+        case RTK_E_DRIVER: return "rtk: cuTensorMapEncodeTiled unavailable or failed";
+        default: return "rtk: unknown error";
+    }
+}
+
+extern "C" int rtk_pivot_rope(const void* x, int64_t heads, int64_t L, int64_t D, int64_t stride_h, int64_t stride_l,
+                              const void* cos, const void* sin, int n_pos, const int32_t* mrope_section_host,
+                              float inv_scale2, int forward, void* out, int64_t out_stride_h, int64_t out_stride_l,
+                              void* stream) {
+    if (!x || !cos || !sin || !out || heads < 1 || L < 1 || D < 16) return RTK_E_BADARG;
+    if (D % 16 != 0 || (n_pos != 1 && n_pos != 3)) return RTK_E_UNSUPPORTED;
+    if (n_pos == 3 && !mrope_section_host) return RTK_E_BADARG;
+    if ((((uintptr_t)x | (uintptr_t)out) & 15u) != 0) return RTK_E_ALIGN;
+    if ((stride_h | stride_l | out_stride_h | out_stride_l) % 8 != 0) return RTK_E_ALIGN;
+    RopeParams p;
+    p.heads = (int)heads; p.L = (int)L; p.D = (int)D; p.n_pos = n_pos; p.forward = forward;
+    p.stride_h = stride_h; p.stride_l = stride_l; p.out_stride_h = out_stride_h; p.out_stride_l = out_stride_l;
+    p.inv_scale2 = inv_scale2;
+    int acc = 0;
+    for (int i = 0; i < 6; ++i) {
+        acc += (n_pos == 3) ? mrope_section_host[i % 3] : 0;
+        p.bound[i] = acc;
+    }
+    if (n_pos == 3 && acc != D) return RTK_E_UNSUPPORTED;
+    const long long total = heads * L * (D / 16);
+    long long grid = (total + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    pivot_rope_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, (__nv_bfloat16*)out, p);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L, const uint8_t* keymask, int64_t keep,
+                                int32_t* keep_idx, void* score_out, void* stream) {
+    if (!head_scores || !keep_idx || KVH < 1 || L < 1 || keep < 1 || keep > L) return RTK_E_BADARG;
+    if (L > 16384) return RTK_E_UNSUPPORTED;
+    const size_t smem = (size_t)L * 4 + 64 * 4;
+    cudaError_t e = cudaFuncSetAttribute(pivot_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pivot_select_kernel<<<1, kSelThreads, smem, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)head_scores, (int)KVH, (int)L, keymask, (int)keep, keep_idx, (__nv_bfloat16*)score_out);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rtk_pivot_compact(const void* k, const void* v, int64_t KVH, int64_t L, int64_t D, int64_t stride_h,
+                                 int64_t stride_l, const int32_t* keep_idx, int64_t keep, void* k_out, void* v_out,
+                                 int64_t out_stride_h, const int64_t* pos, int n_pos, int64_t* pos_out, int reforge,
+                                 void* stream) {
+    if (!k || !v || !keep_idx || !k_out || !v_out || KVH < 1 || L < 1 || D < 8 || keep < 1 || keep > L) return RTK_E_BADARG;
+    if (pos && (!pos_out || n_pos < 1)) return RTK_E_BADARG;
+    if (D % 8 != 0) return RTK_E_UNSUPPORTED;
+    if ((((uintptr_t)k | (uintptr_t)v | (uintptr_t)k_out | (uintptr_t)v_out) & 15u) != 0) return RTK_E_ALIGN;
+    if ((stride_h | stride_l | out_stride_h) % 8 != 0) return RTK_E_ALIGN;
+    CompactParams p;
+    p.KVH = (int)KVH; p.L = (int)L; p.D = (int)D; p.keep = (int)keep; p.n_pos = n_pos; p.reforge = reforge;
+    p.stride_h = stride_h; p.stride_l = stride_l; p.out_stride_h = out_stride_h;
+    p.ratio = (float)((double)keep / (double)L);
+    const long long total = KVH * keep * (D / 8);
+    long long grid = (total + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    pivot_compact_kernel<<<(unsigned)(grid + 1), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, keep_idx, (__nv_bfloat16*)k_out, (__nv_bfloat16*)v_out,
+        (const long long*)pos, (long long*)pos_out, p);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,420 @@
+// PivotKV scoring (sm_100a, tcgen05 + TMEM + TMA).  Replaces retake/longvideo_cache.py:260-269:
+//   S = bf16(Q K^T);  S = bf16(S * f32(1/sqrt D));  P = bf16(softmax_f32(S));  a = bf16(sum_q P);
+//   head_scores = bf16(mean over the G heads of each KV group)
+// without ever materialising an L x L tensor.
+//
+// Column sums of a row-normalised softmax need the row statistics first, so the contraction runs twice:
+//   pass 1 (rows = queries)  D = Q_tile . K_tile^T : per query row the running max / sum  -> c_q = m*log2e + log2(l)
+//   pass 2 (rows = keys)     D = K_tile . Q_tile^T : p = bf16(exp2(s*log2e - c_q)), accumulated per key row
+// In both passes a CTA keeps one 128-row "stationary" tile in shared memory and streams the other operand
+// through a 4-stage TMA ring; accumulators are 128x128 fp32 tiles in TMEM (4 buffers = all 512 columns).
+// Because the softmax side owns whole TMEM lanes, pass 1 reduces along columns inside a thread (no shuffles)
+// and pass 2 accumulates the column sums inside a thread as well - hence the transposed second pass.
+//
+// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
+// warps 2-5 and 6-9 two softmax groups that take alternate accumulator tiles.
+#include <cuda.h>
+
+#include "rtk_common.cuh"
+
+namespace rtk {
+
+constexpr int kTile = 128;            // rows of both operand tiles, = UMMA M = UMMA N
+constexpr int kHeadDim = 128;         // largest D: two 64-element swizzle atoms (D = 64 uses one)
+constexpr int kStages = 4;            // streamed-operand ring
+constexpr int kAccBufs = 4;           // 128-column TMEM buffers
+constexpr int kStatSlots = 8;         // pass 2: per-tile c_q rows (see ring-distance argument in DESIGN.md)
+constexpr int kScoreThreads = 320;
+constexpr uint32_t kTileBytes = kTile * kHeadDim * 2;        // 32 KiB
+constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] swizzle-128B box
+
+struct ScoreSmem {
+    // offsets inside dynamic shared memory (1024-byte aligned base)
+    static constexpr uint32_t a_tile = 0;
+    static constexpr uint32_t b_ring = kTileBytes;
+    static constexpr uint32_t stats = b_ring + kStages * kTileBytes;                 // [kStatSlots][128] f32
+    static constexpr uint32_t merge = stats + kStatSlots * kTile * 4;                // [2][128] f32
+    static constexpr uint32_t bars = merge + 2 * kTile * 4;
+    // barriers: a_full, a_empty, b_full[4], b_empty[4], t_full[4], t_empty[4], st_full[8]
+    static constexpr uint32_t n_bars = 2 + 2 * kStages + 2 * kAccBufs + kStatSlots;
+    static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
+    static constexpr uint32_t total = tmem_ptr + 16;
+};
+
+// ------------------------------------------------------------------------------------------ tcgen05 wrappers
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2f(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// K-major, 128-byte-swizzled operand tile: 8-row groups 1024 B apart (SBO), version 1, layout SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// D fp32, A/B bf16, both K-major, M = N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
+
+struct ScoreParams {
+    int H, G, L, nt;                  // heads, heads per KV group, chunk length, tiles = ceil(L / 128)
+    int n_atoms;                      // D / 64
+    int q_dim1_is_l, k_dim1_is_l;     // tensor-map coordinate order (dims are sorted by stride on the host)
+    float inv_sqrt_d;                 // fp32(1 / fp32(sqrt D))
+    float* stats;                     // [H][nt*128]  c_q (pass 1 output, pass 2 input)
+    float* colsum;                    // [H][nt*128]  fp32 sum over queries of bf16(P) (pass 2 output)
+};
+
+constexpr float kLog2e = 1.4426950408889634f;
+
+template <int PASS>
+__global__ void __launch_bounds__(kScoreThreads, 1)
+pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map, ScoreParams prm) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for the swizzle atoms
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    const uint32_t bar0 = base + ScoreSmem::bars;
+    const uint32_t a_full = bar0, a_empty = bar0 + 8;
+    auto b_full = [&](int s) { return bar0 + 16 + 8 * s; };
+    auto b_empty = [&](int s) { return bar0 + 16 + 8 * (kStages + s); };
+    auto t_full = [&](int b) { return bar0 + 16 + 8 * (2 * kStages + b); };
+    auto t_empty = [&](int b) { return bar0 + 16 + 8 * (2 * kStages + kAccBufs + b); };
+    auto st_full = [&](int i) { return bar0 + 16 + 8 * (2 * kStages + 2 * kAccBufs + i); };
+
+    if (threadIdx.x == 0) {
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
+        for (int s = 0; s < kStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
+        for (int b = 0; b < kAccBufs; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 4); }
+        for (int i = 0; i < kStatSlots; ++i) mbar_init(st_full(i), 1);
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(base + ScoreSmem::tmem_ptr, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + ScoreSmem::tmem_ptr);
+
+    const int nt = prm.nt;
+    const int n_units = prm.H * nt;
+    // the stationary operand is Q in pass 1 and K in pass 2
+    const CUtensorMap* a_map = (PASS == 1) ? &q_map : &k_map;
+    const CUtensorMap* b_map = (PASS == 1) ? &k_map : &q_map;
+    const int a_l1 = (PASS == 1) ? prm.q_dim1_is_l : prm.k_dim1_is_l;
+    const int b_l1 = (PASS == 1) ? prm.k_dim1_is_l : prm.q_dim1_is_l;
+
+    if (warp == 0) {
+        // ===================================================================== TMA producer
+        if (lane == 0) {
+            uint32_t cnt = 0, ucnt = 0;
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ucnt) {
+                const int h = u / nt, ta = u - h * nt;
+                const int a_head = (PASS == 1) ? h : h / prm.G;
+                const int b_head = (PASS == 1) ? h / prm.G : h;
+                mbar_wait(a_empty, (ucnt & 1u) ^ 1u);
+                mbar_arrive_expect_tx(a_full, prm.n_atoms * kHalfBytes);
+                for (int kk = 0; kk < prm.n_atoms; ++kk) {
+                    const int row = ta * kTile;
+                    tma_load_3d(base + ScoreSmem::a_tile + kk * kHalfBytes, a_map, kk * 64, a_l1 ? row : a_head,
+                                a_l1 ? a_head : row, a_full);
+                }
+                for (int tb = 0; tb < nt; ++tb, ++cnt) {
+                    const int s = cnt % kStages;
+                    mbar_wait(b_empty(s), ((cnt / kStages) & 1u) ^ 1u);
+                    mbar_arrive_expect_tx(b_full(s), prm.n_atoms * kHalfBytes);
+                    const uint32_t dst = base + ScoreSmem::b_ring + s * kTileBytes;
+                    for (int kk = 0; kk < prm.n_atoms; ++kk) {
+                        const int row = tb * kTile;
+                        tma_load_3d(dst + kk * kHalfBytes, b_map, kk * 64, b_l1 ? row : b_head, b_l1 ? b_head : row,
+                                    b_full(s));
+                    }
+                    if (PASS == 2) {
+                        // c_q of the 128 streamed queries; slot cnt % 8 was last read for tile cnt - 8, which the
+                        // softmax side finished before MMA(cnt - 4) could start, i.e. before b_empty(s) fired
+                        const int sl = cnt % kStatSlots;
+                        mbar_arrive_expect_tx(st_full(sl), kTile * 4u);
+                        bulk_g2s(base + ScoreSmem::stats + sl * kTile * 4u,
+                                 prm.stats + (size_t)h * nt * kTile + (size_t)tb * kTile, kTile * 4u, st_full(sl));
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ======================================================================= MMA issuer
+        uint32_t cnt = 0, ucnt = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ucnt) {
+            mbar_wait(a_full, ucnt & 1u);
+            for (int tb = 0; tb < nt; ++tb, ++cnt) {
+                const int s = cnt % kStages, b = cnt % kAccBufs;
+                mbar_wait(b_full(s), (cnt / kStages) & 1u);
+                mbar_wait(t_empty(b), ((cnt / kAccBufs) & 1u) ^ 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a0 = base + ScoreSmem::a_tile, b0 = base + ScoreSmem::b_ring + s * kTileBytes;
+                    const int nks = prm.n_atoms * 4;
+#pragma unroll 8
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t off = (ks >> 2) * kHalfBytes + (ks & 3) * 32;
+                        umma_bf16(tmem_base + b * kTile, umma_desc_sw128(a0 + off), umma_desc_sw128(b0 + off), kIdesc,
+                                  ks > 0 ? 1u : 0u);
+                    }
+                    tc_commit(b_empty(s));
+                    tc_commit(t_full(b));
+                    if (tb == nt - 1) tc_commit(a_empty);
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ============================================================ softmax groups (warps 2-5, 6-9)
+        const int sw = warp - 2;                 // 0..7
+        const int grp = sw >> 2;                 // tiles with (cnt & 1) == grp
+        const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
+        const int row = quarter * 32 + lane;     // row of the stationary tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+        float* merge = reinterpret_cast<float*>(smem + ScoreSmem::merge);
+        const float inv = prm.inv_sqrt_d;
+        uint32_t cnt = 0;
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            const int h = u / nt, ta = u - h * nt;
+            float m = -INFINITY, l = 0.f;        // pass 1: running max (scaled-logit domain) and sum
+            float acc0 = 0.f, acc1 = 0.f;        // pass 2: column sums (two interleaved accumulators)
+            for (int tb = 0; tb < nt; ++tb, ++cnt) {
+                if ((int)(cnt & 1u) != grp) continue;
+                const int b = cnt % kAccBufs;
+                mbar_wait(t_full(b), (cnt / kAccBufs) & 1u);
+                tc_fence_after();
+                if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
+                const int valid = prm.L - tb * kTile;        // streamed rows that exist (>= 128 except last tile)
+                const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile;
+#pragma unroll 1
+                for (int c = 0; c < kTile / 32; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(lane_addr + b * kTile + c * 32, r);
+                    tmem_ld_wait();
+                    // reference rounding chain: bf16(acc), then bf16(x * inv_sqrt_d)
+                    float y[32];
+#pragma unroll
+                    for (int i = 0; i < 32; i += 2) {
+                        const uint32_t p1 = pack_bf16x2_rn(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
+                        const uint32_t p2 = pack_bf16x2_rn(bf16lo_to_f32(p1) * inv, bf16hi_to_f32(p1) * inv);
+                        y[i] = bf16lo_to_f32(p2);
+                        y[i + 1] = bf16hi_to_f32(p2);
+                    }
+                    if (PASS == 1) {
+                        if (valid < kTile) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (c * 32 + i >= valid) y[i] = -INFINITY;
+                        }
+                        float mx = y[0];
+#pragma unroll
+                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, y[i]);
+                        const float mn = fmaxf(m, mx);
+                        if (mn > -INFINITY) {
+                            const float mm = mn * kLog2e;
+                            l *= ex2f(fmaf(m, kLog2e, -mm));
+                            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                            for (int i = 0; i < 32; i += 2) {
+                                s0 += ex2f(fmaf(y[i], kLog2e, -mm));
+                                s1 += ex2f(fmaf(y[i + 1], kLog2e, -mm));
+                            }
+                            l += s0 + s1;
+                            m = mn;
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            const float4 cc = *reinterpret_cast<const float4*>(cq + c * 32 + i);
+                            const uint32_t p01 = pack_bf16x2_rn(ex2f(fmaf(y[i], kLog2e, -cc.x)), ex2f(fmaf(y[i + 1], kLog2e, -cc.y)));
+                            const uint32_t p23 = pack_bf16x2_rn(ex2f(fmaf(y[i + 2], kLog2e, -cc.z)), ex2f(fmaf(y[i + 3], kLog2e, -cc.w)));
+                            acc0 += bf16lo_to_f32(p01); acc1 += bf16hi_to_f32(p01);
+                            acc0 += bf16lo_to_f32(p23); acc1 += bf16hi_to_f32(p23);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty(b));
+            }
+            // ---- fold the two groups and write this unit's result
+            if (PASS == 1) {
+                if (grp == 1) { merge[row] = m; merge[kTile + row] = l; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (grp == 0) {
+                    const float m2 = merge[row], l2 = merge[kTile + row];
+                    const float mn = fmaxf(m, m2);
+                    const float mm = mn * kLog2e;
+                    float lt = l * ex2f(fmaf(m, kLog2e, -mm));
+                    if (m2 > -INFINITY) lt += l2 * ex2f(fmaf(m2, kLog2e, -mm));
+                    const int q = ta * kTile + row;
+                    prm.stats[(size_t)h * nt * kTile + q] = (q < prm.L) ? mm + lg2f(lt) : INFINITY;
+                }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            } else {
+                if (grp == 1) merge[row] = acc0 + acc1;
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (grp == 0) prm.colsum[(size_t)h * nt * kTile + ta * kTile + row] = (acc0 + acc1) + merge[row];
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// a = bf16(colsum);  head_scores[g] = bf16((sum over the G heads of group g, ATen 4-accumulator order) * f32(1/G))
+__global__ void pivot_head_reduce_kernel(const float* __restrict__ colsum, int H, int G, int L, int Lpad,
+                                         __nv_bfloat16* __restrict__ head_scores) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = blockIdx.y;
+    if (k >= L) return;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = 0; j < G; ++j) v[j & 3] += round_bf16(colsum[(size_t)(g * G + j) * Lpad + k]);
+    const float s = ((v[0] + v[1]) + v[2]) + v[3];
+    head_scores[(size_t)g * L + k] = __float2bfloat16_rn(s * (1.0f / (float)G));
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// [heads, L, 128] bf16 view with element strides (stride_h, stride_l, 1) -> 3-D map, box = 64 x 128 rows x 1 head.
+// Dimensions 1 and 2 are ordered by ascending stride; *dim1_is_l tells the kernel which coordinate is the row.
+static int make_map(CUtensorMap* map, const void* ptr, int64_t heads, int64_t L, int64_t D, int64_t stride_h,
+                    int64_t stride_l, int* dim1_is_l) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return RTK_E_DRIVER;
+    const bool l_first = (heads == 1) || (stride_l <= stride_h);
+    *dim1_is_l = l_first ? 1 : 0;
+    cuuint64_t dims[3] = {(cuuint64_t)D, (cuuint64_t)(l_first ? L : heads), (cuuint64_t)(l_first ? heads : L)};
+    cuuint64_t strides[2] = {(cuuint64_t)((l_first ? stride_l : stride_h) * 2), (cuuint64_t)((l_first ? stride_h : stride_l) * 2)};
+    if (heads == 1) strides[1] = (cuuint64_t)(stride_l * 2) * (cuuint64_t)L;      // never stepped; keep it well-formed
+    cuuint32_t box[3] = {64u, (cuuint32_t)(l_first ? kTile : 1), (cuuint32_t)(l_first ? 1 : kTile)};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : RTK_E_DRIVER;
+}
+
+}  // namespace rtk
+
+using namespace rtk;
+
+extern "C" size_t rtk_pivot_score_workspace_bytes(int64_t H, int64_t L) {
+    if (H < 1 || L < 1) return 0;
+    const size_t lpad = (size_t)((L + kTile - 1) / kTile) * kTile;
+    return 2 * (size_t)H * lpad * sizeof(float);
+}
+
+extern "C" int rtk_pivot_score(const void* q, int64_t H, int64_t q_stride_h, int64_t q_stride_l, const void* k, int64_t KVH,
+                               int64_t k_stride_h, int64_t k_stride_l, int64_t L, int64_t D, void* head_scores,
+                               void* workspace, size_t workspace_bytes, void* stream) {
+    if (!q || !k || !head_scores || !workspace || H < 1 || KVH < 1 || L < 1) return RTK_E_BADARG;
+    if ((D != 64 && D != 128) || H % KVH != 0 || L > 16384) return RTK_E_UNSUPPORTED;
+    if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)workspace) & 15u) != 0) return RTK_E_ALIGN;
+    if ((q_stride_h | q_stride_l | k_stride_h | k_stride_l) % 8 != 0) return RTK_E_ALIGN;
+    if (workspace_bytes < rtk_pivot_score_workspace_bytes(H, L)) return RTK_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    ScoreParams prm;
+    prm.H = (int)H;
+    prm.G = (int)(H / KVH);
+    prm.L = (int)L;
+    prm.nt = (int)((L + kTile - 1) / kTile);
+    prm.n_atoms = (int)(D / 64);
+    const float sq = (float)sqrt((double)D);
+    prm.inv_sqrt_d = 1.0f / sq;
+    prm.stats = reinterpret_cast<float*>(workspace);
+    prm.colsum = prm.stats + (size_t)H * prm.nt * kTile;
+
+    CUtensorMap qm, km;
+    int rc = make_map(&qm, q, H, L, D, q_stride_h, q_stride_l, &prm.q_dim1_is_l);
+    if (rc) return rc;
+    rc = make_map(&km, k, KVH, L, D, k_stride_h, k_stride_l, &prm.k_dim1_is_l);
+    if (rc) return rc;
+
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int units = prm.H * prm.nt;
+    const int grid = units < sms ? units : sms;
+    const size_t smem = ScoreSmem::total + 1024;
+    cudaError_t e = cudaFuncSetAttribute(pivot_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(pivot_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    pivot_score_kernel<1><<<grid, kScoreThreads, smem, st>>>(qm, km, prm);
+    RTK_CHECK_LAUNCH();
+    pivot_score_kernel<2><<<grid, kScoreThreads, smem, st>>>(qm, km, prm);
+    RTK_CHECK_LAUNCH();
+    dim3 g2((unsigned)((L + 255) / 256), (unsigned)KVH);
+    pivot_head_reduce_kernel<<<g2, 256, 0, st>>>(prm.colsum, (int)H, prm.G, (int)L, prm.nt * kTile,
+                                                 reinterpret_cast<__nv_bfloat16*>(head_scores));
+    RTK_CHECK_LAUNCH();
+    return 0;
+}

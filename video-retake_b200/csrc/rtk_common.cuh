@@ -1,0 +1,118 @@
+// Shared device helpers for the sm_100a kernels (bf16 rounding primitives, mbarrier / bulk-copy PTX,
+// radix-order key transform).  Everything here is header-only and internal to the library.
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/rtk_b200.h"
+
+namespace rtk {
+
+extern long long g_launches;  // host-side launch counter (rtk_launch_count)
+
+#define RTK_CHECK_LAUNCH()                                   \
+    do {                                                     \
+        ++::rtk::g_launches;                                 \
+        cudaError_t e__ = cudaGetLastError();                \
+        if (e__ != cudaSuccess) return (int)e__;             \
+    } while (0)
+
+constexpr int kWarp = 32;
+
+// ---------------------------------------------------------------------------------------------- bf16 bits
+// A bf16 value widened to fp32 is its 16 bits in the upper half of the word.
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+
+// cvt.rn.bf16x2.f32 d, a, b : d.hi = bf16(a), d.lo = bf16(b)   (round to nearest even, one instruction)
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float lo, float hi) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+    return d;
+}
+__device__ __forceinline__ float round_bf16(float x) {  // fp32 -> bf16 (RN) -> fp32
+    return __bfloat162float(__float2bfloat16_rn(x));
+}
+// exact bf16 product pair: RN(a*b) per half (the fp32 product of two bf16 is exact, so this equals ATen's
+// float multiply followed by the bf16 cast)
+__device__ __forceinline__ uint32_t mul_bf16x2_rn(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+// Radix order used by ATen's CUDA top-k (SortingRadixSelect.cuh TopKTypeConfig<float>): NaN is the largest
+// key, -0 sorts below +0.
+__device__ __forceinline__ uint32_t f32_to_ordered(float v) {
+    uint32_t x = __float_as_uint(v);
+    uint32_t mask = (x & 0x80000000u) ? 0xffffffffu : 0x80000000u;
+    return (v == v) ? (x ^ mask) : 0xffffffffu;
+}
+
+// ------------------------------------------------------------------------------- mbarrier / bulk async copy
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// 1-D bulk copy global -> shared (TMA engine, SASS UBLKCP); bytes % 16 == 0, both sides 16-byte aligned.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+// 1-D bulk copy shared -> global.
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+}  // namespace rtk

@@ -1,0 +1,78 @@
+"""ctypes binding of ``librtk_b200.so`` (``include/rtk_b200.h``).
+
+The library is the product: there is no fallback.  If it is missing, or a tensor is not a CUDA
+tensor, the call raises - nothing here ever computes on the host or through stock torch ops.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("RTK_B200_LIB", os.path.join(os.path.dirname(_HERE), "lib", "librtk_b200.so"))
+
+_lib = None
+
+
+class RtkError(RuntimeError):
+    pass
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RtkError(
+            f"{LIB_PATH} not found: build it with `python video-retake_b200/build.py` "
+            "(nvcc, sm_100a). There is no CPU or stock-PyTorch fallback for this path."
+        )
+    L = C.CDLL(LIB_PATH)
+    p, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
+    sig = {
+        "rtk_version": ([], C.c_int),
+        "rtk_error_string": ([C.c_int], C.c_char_p),
+        "rtk_launch_count": ([], i64),
+        "rtk_dpselect_dis": ([p, i64, i64, i64, i32, p, p], C.c_int),
+        "rtk_dpselect_select": ([p, i64, i64, i64, i32, p, p, p], C.c_int),
+        "rtk_dpselect_gather": ([p, i64, i64, i64, p, i64, i32, p, p], C.c_int),
+        "rtk_pivot_rope": ([p, i64, i64, i64, i64, i64, p, p, i32, p, f32, i32, p, i64, i64, p], C.c_int),
+        "rtk_pivot_score_workspace_bytes": ([i64, i64], sz),
+        "rtk_pivot_score": ([p, i64, i64, i64, p, i64, i64, i64, i64, i64, p, p, sz, p], C.c_int),
+        "rtk_pivot_select": ([p, i64, i64, p, i64, p, p, p], C.c_int),
+        "rtk_pivot_compact": ([p, p, i64, i64, i64, i64, i64, p, i64, p, p, i64, p, i32, p, i32, p], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)            # AttributeError here == header and library disagree
+        fn.argtypes, fn.restype = args, res
+    if L.rtk_version() != 1:
+        raise RtkError(f"ABI mismatch: library reports version {L.rtk_version()}, binding expects 1")
+    _lib = L
+    return L
+
+
+EXPORTS = ("rtk_version", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
+           "rtk_dpselect_gather", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
+           "rtk_pivot_select", "rtk_pivot_compact")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RtkError(f"{what} failed: {lib().rtk_error_string(rc).decode()} (code {rc})")
+
+
+def require_cuda(t: torch.Tensor, name: str, dtype=None) -> None:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RtkError(f"{name} must be a CUDA tensor: this path has no CPU implementation")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(lib().rtk_launch_count())
