@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py - 2048-frame DPSelect + PivotKV throughput (frames/s) on B200.
+
+A "step" is one pass of the hot path over one synthetic 2048-frame Qwen2-VL-7B-shape video:
+  DPSelect  memory_bank_compress_keyframe on X[1, T=1024, N=256, C=3584] bf16 (per-patch mode)
+  PivotKV   PivotKVCache.update for 64 prefill chunks x 28 layers, L = 4096 tokens per chunk, H = 28, KVH = 4, D = 128
+with the shipped recipe of the reference (configs/qwen2_vl/retake_qwen2-vl_mlvu.yaml): visual ratio 1.0 (mask only,
+identity compaction), dynamic KV ratio 32000 / 262144 = 0.122 (keep 499 of 4096), pos_embed_reforge on.
+
+  value  frames / s with every input already resident in HBM, through the public operators
+  e2e    the same through the same operators with the inputs in pinned HOST memory: the H2D copy of the step's
+         inputs and a D2H read of the step's result are inside the timed region
+  roofline      the tcgen05 scoring launches (the dominant kernels), CUDA-event timed inside the timed region
+  cpu_baseline  the reference's own torch-op sequence (oracle/reference_ops.py) on the host cores, bounded sample
+
+--impl reference times that CPU op sequence alone (rank 0 only).  N > 1: one video per rank (weak scaling, no
+data-path collective), torchrun launch.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "video-retake_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "2048-frame DPSelect+PivotKV frames/s"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=2048)
+    ap.add_argument("--visual-ratio", type=float, default=1.0)
+    ap.add_argument("--kv-ratio", type=float, default=-1.0, help="-1: dynamic, 32000 / video tokens (shipped recipe)")
+    ap.add_argument("--no-reforge", action="store_true")
+    ap.add_argument("--pool", type=int, default=16, help="distinct Q/K/V sets cycled through the layer-chunks")
+    ap.add_argument("--layers", type=int, default=28)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+class Shape:
+    """Qwen2-VL-7B shape at 448x448."""
+
+    def __init__(self, a):
+        self.frames = a.frames
+        self.T = a.frames // 2            # temporal_patch_size 2
+        self.N, self.C = 256, 3584
+        self.H, self.KVH, self.D = 28, 4, 128
+        self.layers = a.layers
+        self.L = min(32, self.T) * 1024 // 8            # chunked_prefill_frames 32 -> 4096 tokens
+        self.t = max(1, round(a.visual_ratio * self.T))
+        self.tokens = self.t * self.N
+        self.chunks = (self.tokens + self.L - 1) // self.L
+        self.kv_ratio = a.kv_ratio if a.kv_ratio > 0 else min(1.0, 32000 / self.tokens)
+        self.keep = max(1, int(self.kv_ratio * self.L))
+        self.reforge = not a.no_reforge
+        self.mrope = [16, 24, 24]
+
+
+def make_rotary(device):
+    from transformers.models.qwen2_vl.configuration_qwen2_vl import Qwen2VLTextConfig
+    from transformers.models.qwen2_vl.modeling_qwen2_vl import Qwen2VLRotaryEmbedding
+    tc = Qwen2VLTextConfig(hidden_size=3584, num_attention_heads=28, num_key_value_heads=4, num_hidden_layers=28,
+                           max_position_embeddings=32768,
+                           rope_parameters={"rope_type": "yarn", "factor": 4.0, "beta_fast": 32.0, "beta_slow": 1.0,
+                                            "rope_theta": 1e6, "mrope_section": [16, 24, 24],
+                                            "original_max_position_embeddings": 32768})
+    return Qwen2VLRotaryEmbedding(tc).to(device)
+
+
+def cache_config(s):
+    import types
+    cfg = types.SimpleNamespace(hidden_size=s.H * s.D, num_hidden_layers=s.layers, num_attention_heads=s.H,
+                                num_key_value_heads=s.KVH)
+    cfg.longvideo_kwargs = {"kvcache_compression": True,
+                            "kvcache_compression_kwargs": {"compression_ratio": s.kv_ratio, "compression_method": "pivotkv",
+                                                           "pos_embed_reforge": s.reforge}}
+    return cfg
+
+
+def synth_host(s, pool, seed):
+    """pinned host inputs: scene-structured embeddings + a pool of Q/K/V sets in the attention layout [1, L, heads, D]"""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.empty(s.T, s.N, s.C, dtype=torch.bfloat16)
+    t = 0
+    while t < s.T:                                         # x[t] = scene + 0.3 * noise, scenes of 3..40 grids
+        run = int(torch.randint(3, 41, (1,), generator=g))
+        scene = torch.randn(s.N, s.C, generator=g)
+        for _ in range(run):
+            if t >= s.T:
+                break
+            x[t] = (scene + 0.3 * torch.randn(s.N, s.C, generator=g)).to(torch.bfloat16)
+            t += 1
+    q = torch.randn(pool, s.L, s.H, s.D, generator=g).to(torch.bfloat16)
+    k = torch.randn(pool, s.L, s.KVH, s.D, generator=g).to(torch.bfloat16)
+    v = torch.randn(pool, s.L, s.KVH, s.D, generator=g).to(torch.bfloat16)
+    if torch.cuda.is_available():
+        return [t_.pin_memory() for t_ in (x, q, k, v)]
+    return [x, q, k, v]
+
+
+class ScoreTimer:
+    """CUDA-event pairs around a sample of the rtk_pivot_score calls inside the timed region."""
+
+    def __init__(self, every=8):
+        self.every, self.n, self.pairs = every, 0, []
+        self.on = False
+
+    def install(self, lc):
+        inner = lc.pivot_head_scores
+        timer = self
+
+        def timed(q, k):
+            timer.n += 1
+            if not timer.on or timer.n % timer.every:
+                return inner(q, k)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            out = inner(q, k)
+            b.record()
+            timer.pairs.append((a, b))
+            return out
+        lc.pivot_head_scores = timed
+
+    def mean_ms(self):
+        return sum(a.elapsed_time(b) for a, b in self.pairs) / max(1, len(self.pairs))
+
+
+def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid):
+    """one video through the public operators; returns a small device tensor standing for the step's result"""
+    out, mask = vc.memory_bank_compress_keyframe(x[None], s.t, 3, sync=False)
+    cache = lc.build_kvcache(cache_config(s))
+    pool = q.shape[0]
+    it = 0
+    for c in range(s.chunks):
+        ss, ee = c * s.L, min((c + 1) * s.L, s.tokens)
+        Lc = ee - ss
+        cache.kvcache_compression = True
+        cache.keypatches_mask_chunk = mask[ss:ee]
+        for layer in range(s.layers):
+            j = it % pool
+            it += 1
+            pos = pos_grid[:, :, :Lc].clone()
+            if s.reforge:
+                pos[0] += cache.get_prev_temporal_idx(layer) + 1
+            else:
+                pos[0] += c * (s.L // s.N)
+            cache.update(k[j:j + 1, :Lc].transpose(1, 2), v[j:j + 1, :Lc].transpose(1, 2), layer,
+                         {"query_states": q[j:j + 1, :Lc].transpose(1, 2), "position_ids": pos, "rotary_emb": rotary,
+                          "mrope_section": s.mrope})
+    return cache.last_keep_indices, cache.get_seq_length(0)
+
+
+def clocks_sampler(dev_index):
+    try:
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        return subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                 "-i", str(dev_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return None
+
+
+def clocks_summary(proc):
+    if proc is None:
+        return None
+    proc.terminate()
+    try:
+        text, _ = proc.communicate(timeout=5)
+    except Exception:
+        return None
+    sm, mx, reasons = [], 0.0, set()
+    for line in text.strip().splitlines():
+        f = [z.strip() for z in line.split(",")]
+        if len(f) < 9:
+            continue
+        try:
+            sm.append(float(f[1]))
+            mx = max(mx, float(f[2]))
+        except ValueError:
+            continue
+        for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+            if val.lower().startswith("active"):
+                reasons.add(name)
+    if not sm:
+        return None
+    sm.sort()
+    return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step(s, sample_T, host, it):
+    """bounded sample of the reference's CPU op sequence: DPSelect on sample_T grids + ONE compressing update at the
+    real chunk length; returns seconds extrapolated to the whole video (cost is linear in grids and in layer-chunks)."""
+    from oracle import reference_ops as ro
+    from helpers import TableRotary
+    x, q, k, v = host
+    t0 = time.perf_counter()
+    tt = max(1, round(sample_T * s.t / s.T))
+    out, mask, _ = ro.dpselect(x[None, :sample_T], tt, False)
+    t1 = time.perf_counter()
+    j = it % q.shape[0]
+    rot = TableRotary(s.D)
+    pos = torch.stack([torch.arange(s.L) // s.N, (torch.arange(s.L) % s.N) // 16, torch.arange(s.L) % 16])[:, None]
+    ro.pivot_update(q[j:j + 1].transpose(1, 2), k[j:j + 1].transpose(1, 2), v[j:j + 1].transpose(1, 2), s.kv_ratio,
+                    mask[:s.L] if mask.numel() >= s.L else None, pos, rot, s.mrope, s.reforge)
+    t2 = time.perf_counter()
+    return (t1 - t0) * (s.T / sample_T) + (t2 - t1) * s.chunks * s.layers, (t1 - t0), (t2 - t1)
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    s = Shape(a)
+    workload = (f"Qwen2-VL-7B-shape {s.frames} frames @448px: DPSelect X[1,{s.T},{s.N},{s.C}] r_v={s.t / s.T:.3g} "
+                f"patch_sync=False + PivotKV {s.chunks} chunks x {s.layers} layers, L={s.L}, H={s.H}, KVH={s.KVH}, "
+                f"D={s.D}, r_kv={s.kv_ratio:.4g} (keep {s.keep}), reforge={s.reforge}")
+    config = {"workload": workload, "frames": s.frames, "visual_ratio": s.t / s.T, "kv_ratio": s.kv_ratio,
+              "pos_embed_reforge": s.reforge, "qkv_pool": a.pool,
+              "l2_policy": "inputs larger than L2 (X 1.9 GB; Q/K/V pool cycled, reuse distance > 126 MB)",
+              "parallelism": f"dp{world} (one video per GPU, no data-path collective)"}
+
+    if a.impl == "reference":
+        if rank != 0:
+            return
+        torch.set_num_threads(os.cpu_count())
+        host = synth_host(s, 2, 1234)
+        sample_T = 64
+        times = []
+        for i in range(a.warmup + a.steps):
+            t, td, tu = cpu_reference_step(s, sample_T, host, i)
+            if i >= a.warmup:
+                times.append(t)
+        sec = sum(times) / len(times)
+        val = s.frames / sec
+        sample = (f"per step: DPSelect on {sample_T} of {s.T} temporal grids + 1 of {s.chunks * s.layers} compressing updates "
+                  f"at L={s.L}, scaled linearly to the whole video (extrapolated)")
+        print(json.dumps({"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+                          "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "bf16", "data": "synthetic", "impl": "reference", "config": config,
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "gpu_launches": 0}))
+        return
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (there is no CPU path for --impl b200)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    from retake import _native
+    from retake import longvideo_cache as lc
+    from retake import visual_compression as vc
+    timer = ScoreTimer()
+    timer.install(lc)
+    rotary = make_rotary(dev)
+    host = synth_host(s, a.pool, 1234 + rank)
+    x, q, k, v = [h.to(dev, non_blocking=True) for h in host]
+    ar = torch.arange(s.L, device=dev)
+    pos_grid = torch.stack([ar // s.N, (ar % s.N) // 16, ar % 16])[:, None]
+    torch.cuda.synchronize()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(a.warmup):
+        run_step(s, x, q, k, v, rotary, lc, vc, pos_grid)
+    sync_all()
+    sampler = clocks_sampler(local_rank) if rank == 0 else None
+    launches0 = _native.launch_count()
+    timer.on = True
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        res = run_step(s, x, q, k, v, rotary, lc, vc, pos_grid)
+    e1.record()
+    sync_all()
+    timer.on = False
+    launches = _native.launch_count() - launches0
+    clocks = clocks_summary(sampler)
+    ms = e0.elapsed_time(e1)
+    if dist is not None:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t)
+    ms_per_step = ms / a.steps
+    value = world * s.frames / (ms_per_step * 1e-3)
+
+    # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region
+    e2e = None
+    if not a.no_e2e:
+        h2d = sum(h.numel() * h.element_size() for h in host)
+        xd, qd, kd, vd = [torch.empty_like(h, device=dev) for h in host]
+        sync_all()
+        e0.record()
+        d2h = 0
+        for _ in range(a.steps):
+            for dst, src in zip((xd, qd, kd, vd), host):
+                dst.copy_(src, non_blocking=True)
+            keep_idx, seq = run_step(s, xd, qd, kd, vd, rotary, lc, vc, pos_grid)
+            back = keep_idx.cpu()
+            d2h = back.numel() * back.element_size()
+        e1.record()
+        sync_all()
+        ems = e0.elapsed_time(e1)
+        if dist is not None:
+            t = torch.tensor([ems], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ems = float(t)
+        e2e = {"value": world * s.frames / (ems / a.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h}
+        del xd, qd, kd, vd
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1.4 PFLOP/s sustained (of fallback)"
+    score_ms = timer.mean_ms()
+    flops = 2.0 * s.H * s.L * s.L * s.D
+    achieved = flops / (score_ms * 1e-3) / 1e12 if score_ms > 0 else 0.0
+    roofline = {"kernel": "pivot_score_kernel<1> + pivot_score_kernel<2> (one rtk_pivot_score call)", "bound": "tensor",
+                "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "achieved_executed": 2 * achieved, "frac_executed": 2 * achieved / peak_tf, "peak_source": peak_src,
+                "ms_per_call": score_ms, "calls_timed": len(timer.pairs), "traffic": None,
+                "note": "algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it twice"}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "config": config, "roofline": roofline, "gpu_launches": int(launches)}
+    if e2e is not None:
+        line["e2e"] = e2e
+    if clocks is not None:
+        line["clocks"] = clocks
+    if world == 1 and not a.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        cpu_host = [h[:2] if i else h for i, h in enumerate(host)]
+        cpu_reference_step(s, 16, cpu_host, 0)                      # warm the CPU path
+        sec, td, tu = cpu_reference_step(s, 64, cpu_host, 1)
+        line["cpu_baseline"] = {"value": s.frames / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": (f"DPSelect on 64 of {s.T} grids ({td:.2f} s) + 1 of {s.chunks * s.layers} compressing "
+                                           f"updates at L={s.L} ({tu:.2f} s), scaled linearly (extrapolated)")}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -175,3 +175,30 @@ def test_cuda_and_cpu_semantics_differ_only_in_last_bit():
     b = op.pivot_scores(st["q"], st["k"], "cuda").float()
     assert float(((a - b).abs() / a.abs().clamp_min(1e-6)).max()) <= 2 ** -7
     assert abs(float(a.mean()) - 1.0) < 0.02                      # scores average 1 per key (note N3)
+
+
+# ------------------------------------------------------------- second oracle form: the reference's own op sequence
+from oracle import reference_ops as ro  # noqa: E402
+
+
+@pytest.mark.parametrize("case", DP, ids=_id)
+def test_reference_ops_dpselect_bit_identical(case):
+    out, mask, _ = ro.dpselect(case["x"], case["t"], case["sync"])
+    assert torch.equal(mask, case["mask"]) and torch.equal(out, case["out"])
+
+
+@pytest.mark.parametrize("case", REPLAY, ids=lambda c: c["name"])
+def test_reference_ops_pivot_update_bit_identical(case):
+    """first chunk of every layer (empty past): cache == kept K/V/positions, all dtypes incl. bf16"""
+    rot = TableRotary(**case["rotary"])
+    n = 0
+    for st in case["steps"]:
+        if st["chunk"] != 0:
+            continue
+        kk, vv, pos, idx, _ = ro.pivot_update(st["q"], st["k"], st["v"], case["ratio"], st["mask"], st["pos"].clone(),
+                                              rot, case["mrope"], case["reforge"])
+        assert torch.equal(kk, st["key_cache"]) and torch.equal(vv, st["value_cache"])
+        if case["reforge"]:
+            assert torch.equal(pos, st["position_cache"])
+        n += 1
+    assert n >= 1

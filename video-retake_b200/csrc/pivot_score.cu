@@ -24,7 +24,6 @@ constexpr int kHeadDim = 128;         // largest D: two 64-element swizzle atoms
 constexpr int kStages = 4;            // streamed-operand ring
 constexpr int kAccBufs = 4;           // 128-column TMEM buffers
 constexpr int kStatSlots = 8;         // pass 2: per-tile c_q rows (see ring-distance argument in DESIGN.md)
-constexpr int kScoreThreads = 320;
 constexpr uint32_t kTileBytes = kTile * kHeadDim * 2;        // 32 KiB
 constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] swizzle-128B box
 
@@ -33,8 +32,8 @@ struct ScoreSmem {
     static constexpr uint32_t a_tile = 0;
     static constexpr uint32_t b_ring = kTileBytes;
     static constexpr uint32_t stats = b_ring + kStages * kTileBytes;                 // [kStatSlots][128] f32
-    static constexpr uint32_t merge = stats + kStatSlots * kTile * 4;                // [2][128] f32
-    static constexpr uint32_t bars = merge + 2 * kTile * 4;
+    static constexpr uint32_t merge = stats + kStatSlots * kTile * 4;                // [4][128][2] f32
+    static constexpr uint32_t bars = merge + 4 * kTile * 2 * 4;
     // barriers: a_full, a_empty, b_full[4], b_empty[4], t_full[4], t_empty[4], st_full[8]
     static constexpr uint32_t n_bars = 2 + 2 * kStages + 2 * kAccBufs + kStatSlots;
     static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
@@ -106,14 +105,75 @@ struct ScoreParams {
     int n_atoms;                      // D / 64
     int q_dim1_is_l, k_dim1_is_l;     // tensor-map coordinate order (dims are sorted by stride on the host)
     float inv_sqrt_d;                 // fp32(1 / fp32(sqrt D))
-    float* stats;                     // [H][nt*128]  c_q (pass 1 output, pass 2 input)
-    float* colsum;                    // [H][nt*128]  fp32 sum over queries of bf16(P) (pass 2 output)
+    float2* ml_part;                  // [2][H][nt*128]  pass 1 partial (row max in scaled-logit domain, row sum)
+    float* stats;                     // [H][nt*128]     c_q = m*log2e + log2(l)   (merge kernel output, pass 2 input)
+    float* colsum_part;               // [2][H][nt*128]  pass 2 partial fp32 sums over queries of bf16(P)
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
 
+// ------------------------------------------------------------------------------- packed fp32x2 helpers (sm_100)
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t d;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(lo), "f"(hi));
+    return d;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+// bf16x2 -> (lo, hi) widened to fp32, packed for the x2 pipes
+__device__ __forceinline__ uint64_t widen2(uint32_t p) { return pk2(bf16lo_to_f32(p), bf16hi_to_f32(p)); }
+
+// the reference's logit rounding chain on a pair of raw accumulators: bf16(acc) then bf16(x * inv_sqrt_d); fp32 out
+__device__ __forceinline__ uint64_t logit_chain2(uint32_t r0, uint32_t r1, uint64_t inv2) {
+    const uint32_t p1 = pack_bf16x2_rn(__uint_as_float(r0), __uint_as_float(r1));
+    float s0, s1;
+    upk2(mul2(widen2(p1), inv2), s0, s1);
+    return widen2(pack_bf16x2_rn(s0, s1));
+}
+__device__ __forceinline__ float logit_chain1(float acc, float inv) { return round_bf16(round_bf16(acc) * inv); }
+
+// One CTA's share of the flattened (unit, streamed tile) space: a contiguous range, so every SM gets the same
+// number of tile-steps (+-1) and a unit is shared by at most two CTAs (range length >= nt).
+struct TileRange {
+    long long g, g1;
+    int nt;
+    __device__ __forceinline__ TileRange(int H, int nt_) : nt(nt_) {
+        const long long G = (long long)H * nt_ * nt_;
+        g = G * blockIdx.x / gridDim.x;
+        g1 = G * (blockIdx.x + 1) / gridDim.x;
+    }
+    __device__ __forceinline__ bool next(int& u, int& tb0, int& tb1) {
+        if (g >= g1) return false;
+        u = (int)(g / nt);
+        tb0 = (int)(g - (long long)u * nt);
+        const long long left = g1 - g;
+        tb1 = (left < nt - tb0) ? tb0 + (int)left : nt;
+        g += tb1 - tb0;
+        return true;
+    }
+};
+
+constexpr int kSoftmaxWarps = 16;     // four groups of four warps (one per TMEM lane quarter)
+constexpr int kScoreThreads2 = (2 + kSoftmaxWarps) * 32;
+
 template <int PASS>
-__global__ void __launch_bounds__(kScoreThreads, 1)
+__global__ void __launch_bounds__(kScoreThreads2, 1)
 pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map, ScoreParams prm) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for the swizzle atoms
@@ -133,7 +193,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int b = 0; b < kAccBufs; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 4); }
+        for (int b = 0; b < kAccBufs; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 8); }
         for (int i = 0; i < kStatSlots; ++i) mbar_init(st_full(i), 1);
         fence_mbar_init();
     }
@@ -144,18 +204,20 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + ScoreSmem::tmem_ptr);
 
     const int nt = prm.nt;
-    const int n_units = prm.H * nt;
+    const size_t hl = (size_t)prm.H * nt * kTile;            // elements of one [H][Lpad] plane
     // the stationary operand is Q in pass 1 and K in pass 2
     const CUtensorMap* a_map = (PASS == 1) ? &q_map : &k_map;
     const CUtensorMap* b_map = (PASS == 1) ? &k_map : &q_map;
     const int a_l1 = (PASS == 1) ? prm.q_dim1_is_l : prm.k_dim1_is_l;
     const int b_l1 = (PASS == 1) ? prm.k_dim1_is_l : prm.q_dim1_is_l;
+    TileRange range(prm.H, nt);
+    int u, tb0, tb1;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             uint32_t cnt = 0, ucnt = 0;
-            for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ucnt) {
+            while (range.next(u, tb0, tb1)) {
                 const int h = u / nt, ta = u - h * nt;
                 const int a_head = (PASS == 1) ? h : h / prm.G;
                 const int b_head = (PASS == 1) ? h / prm.G : h;
@@ -166,7 +228,8 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                     tma_load_3d(base + ScoreSmem::a_tile + kk * kHalfBytes, a_map, kk * 64, a_l1 ? row : a_head,
                                 a_l1 ? a_head : row, a_full);
                 }
-                for (int tb = 0; tb < nt; ++tb, ++cnt) {
+                ++ucnt;
+                for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                     const int s = cnt % kStages;
                     mbar_wait(b_empty(s), ((cnt / kStages) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(b_full(s), prm.n_atoms * kHalfBytes);
@@ -190,9 +253,10 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
     } else if (warp == 1) {
         // ======================================================================= MMA issuer
         uint32_t cnt = 0, ucnt = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++ucnt) {
+        while (range.next(u, tb0, tb1)) {
             mbar_wait(a_full, ucnt & 1u);
-            for (int tb = 0; tb < nt; ++tb, ++cnt) {
+            ++ucnt;
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 const int s = cnt % kStages, b = cnt % kAccBufs;
                 mbar_wait(b_full(s), (cnt / kStages) & 1u);
                 mbar_wait(t_empty(b), ((cnt / kAccBufs) & 1u) ^ 1u);
@@ -208,77 +272,75 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                     }
                     tc_commit(b_empty(s));
                     tc_commit(t_full(b));
-                    if (tb == nt - 1) tc_commit(a_empty);
+                    if (tb == tb1 - 1) tc_commit(a_empty);
                 }
                 __syncwarp();
             }
         }
     } else {
-        // ============================================================ softmax groups (warps 2-5, 6-9)
-        const int sw = warp - 2;                 // 0..7
-        const int grp = sw >> 2;                 // tiles with (cnt & 1) == grp
+        // ================================== softmax: 4 groups x 4 warps; tile n -> groups 2*(n&1), 2*(n&1)+1 (column halves)
+        const int sw = warp - 2;                 // 0..15
+        const int grp = sw >> 2;                 // 0..3
         const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
         const int row = quarter * 32 + lane;     // row of the stationary tile
-        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-        float* merge = reinterpret_cast<float*>(smem + ScoreSmem::merge);
+        const int half = grp & 1;                // which 64 columns of the tile
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * 64;
+        float* merge = reinterpret_cast<float*>(smem + ScoreSmem::merge);        // [4][128][2]
         const float inv = prm.inv_sqrt_d;
+        const uint64_t inv2 = pk2(inv, inv), l2e2 = pk2(kLog2e, kLog2e);
         uint32_t cnt = 0;
-        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        while (range.next(u, tb0, tb1)) {
             const int h = u / nt, ta = u - h * nt;
-            float m = -INFINITY, l = 0.f;        // pass 1: running max (scaled-logit domain) and sum
-            float acc0 = 0.f, acc1 = 0.f;        // pass 2: column sums (two interleaved accumulators)
-            for (int tb = 0; tb < nt; ++tb, ++cnt) {
-                if ((int)(cnt & 1u) != grp) continue;
+            float m = -INFINITY;                 // pass 1: running max (scaled-logit domain)
+            uint64_t acc = pk2(0.f, 0.f);        // pass 1: row sum, pass 2: column sum (two interleaved halves)
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                if ((int)(cnt & 1u) != (grp >> 1)) continue;
                 const int b = cnt % kAccBufs;
                 mbar_wait(t_full(b), (cnt / kAccBufs) & 1u);
                 tc_fence_after();
                 if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
-                const int valid = prm.L - tb * kTile;        // streamed rows that exist (>= 128 except last tile)
-                const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile;
+                const int valid = prm.L - tb * kTile - half * 64;      // streamed rows of this half that exist
+                const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + half * 64;
 #pragma unroll 1
-                for (int c = 0; c < kTile / 32; ++c) {
+                for (int c = 0; c < 2; ++c) {
                     uint32_t r[32];
                     tmem_ld32(lane_addr + b * kTile + c * 32, r);
                     tmem_ld_wait();
-                    // reference rounding chain: bf16(acc), then bf16(x * inv_sqrt_d)
-                    float y[32];
-#pragma unroll
-                    for (int i = 0; i < 32; i += 2) {
-                        const uint32_t p1 = pack_bf16x2_rn(__uint_as_float(r[i]), __uint_as_float(r[i + 1]));
-                        const uint32_t p2 = pack_bf16x2_rn(bf16lo_to_f32(p1) * inv, bf16hi_to_f32(p1) * inv);
-                        y[i] = bf16lo_to_f32(p2);
-                        y[i + 1] = bf16hi_to_f32(p2);
-                    }
                     if (PASS == 1) {
-                        if (valid < kTile) {
+                        if (valid < 64) {
 #pragma unroll
                             for (int i = 0; i < 32; ++i)
-                                if (c * 32 + i >= valid) y[i] = -INFINITY;
+                                if (c * 32 + i >= valid) r[i] = 0xff800000u;     // -inf: padded key column
                         }
-                        float mx = y[0];
+                        // the rounding chain is monotone, so the row max of the rounded logits is the chain of the raw max
+                        float mx = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
 #pragma unroll
-                        for (int i = 1; i < 32; ++i) mx = fmaxf(mx, y[i]);
-                        const float mn = fmaxf(m, mx);
+                        for (int i = 3; i < 31; i += 2)
+                            mx = fmaxf(fmaxf(mx, __uint_as_float(r[i])), __uint_as_float(r[i + 1]));
+                        mx = fmaxf(mx, __uint_as_float(r[31]));
+                        const float mn = fmaxf(m, logit_chain1(mx, inv));
                         if (mn > -INFINITY) {
                             const float mm = mn * kLog2e;
-                            l *= ex2f(fmaf(m, kLog2e, -mm));
-                            float s0 = 0.f, s1 = 0.f;
+                            const float sc = ex2f(fmaf(m, kLog2e, -mm));           // m == -inf -> 0
+                            acc = mul2(acc, pk2(sc, sc));
+                            const uint64_t nmm = pk2(-mm, -mm);
 #pragma unroll
                             for (int i = 0; i < 32; i += 2) {
-                                s0 += ex2f(fmaf(y[i], kLog2e, -mm));
-                                s1 += ex2f(fmaf(y[i + 1], kLog2e, -mm));
+                                float y0, y1;
+                                upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), y0, y1);
+                                acc = add2(acc, pk2(ex2f(y0), ex2f(y1)));
                             }
-                            l += s0 + s1;
                             m = mn;
                         }
                     } else {
 #pragma unroll
                         for (int i = 0; i < 32; i += 4) {
                             const float4 cc = *reinterpret_cast<const float4*>(cq + c * 32 + i);
-                            const uint32_t p01 = pack_bf16x2_rn(ex2f(fmaf(y[i], kLog2e, -cc.x)), ex2f(fmaf(y[i + 1], kLog2e, -cc.y)));
-                            const uint32_t p23 = pack_bf16x2_rn(ex2f(fmaf(y[i + 2], kLog2e, -cc.z)), ex2f(fmaf(y[i + 3], kLog2e, -cc.w)));
-                            acc0 += bf16lo_to_f32(p01); acc1 += bf16hi_to_f32(p01);
-                            acc0 += bf16lo_to_f32(p23); acc1 += bf16hi_to_f32(p23);
+                            float y0, y1, y2, y3;
+                            upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y)), y0, y1);
+                            upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w)), y2, y3);
+                            acc = add2(acc, widen2(pack_bf16x2_rn(ex2f(y0), ex2f(y1))));
+                            acc = add2(acc, widen2(pack_bf16x2_rn(ex2f(y2), ex2f(y3))));
                         }
                     }
                 }
@@ -286,25 +348,39 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty(b));
             }
-            // ---- fold the two groups and write this unit's result
+            // ---- fold the four groups and write this CTA's share of the unit
+            float a0, a1;
+            upk2(acc, a0, a1);
+            const int part = (tb0 == 0) ? 0 : 1;
+            const bool whole = (tb0 == 0) && (tb1 == nt);
+            const size_t o = (size_t)h * nt * kTile + (size_t)ta * kTile + row;
             if (PASS == 1) {
-                if (grp == 1) { merge[row] = m; merge[kTile + row] = l; }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                merge[(grp * kTile + row) * 2] = m;
+                merge[(grp * kTile + row) * 2 + 1] = a0 + a1;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
                 if (grp == 0) {
-                    const float m2 = merge[row], l2 = merge[kTile + row];
-                    const float mn = fmaxf(m, m2);
-                    const float mm = mn * kLog2e;
-                    float lt = l * ex2f(fmaf(m, kLog2e, -mm));
-                    if (m2 > -INFINITY) lt += l2 * ex2f(fmaf(m2, kLog2e, -mm));
-                    const int q = ta * kTile + row;
-                    prm.stats[(size_t)h * nt * kTile + q] = (q < prm.L) ? mm + lg2f(lt) : INFINITY;
+                    float mn = -INFINITY;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) mn = fmaxf(mn, merge[(g * kTile + row) * 2]);
+                    float lt = 0.f;
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const float mg = merge[(g * kTile + row) * 2];
+                        if (mg > -INFINITY) lt += merge[(g * kTile + row) * 2 + 1] * ex2f((mg - mn) * kLog2e);
+                    }
+                    prm.ml_part[(size_t)part * hl + o] = make_float2(mn, lt);
+                    if (whole) prm.ml_part[hl + o] = make_float2(-INFINITY, 0.f);
                 }
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                asm volatile("bar.sync 1, 512;" ::: "memory");
             } else {
-                if (grp == 1) merge[row] = acc0 + acc1;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                if (grp == 0) prm.colsum[(size_t)h * nt * kTile + ta * kTile + row] = (acc0 + acc1) + merge[row];
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                merge[grp * kTile + row] = a0 + a1;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                if (grp == 0) {
+                    prm.colsum_part[(size_t)part * hl + o] =
+                        ((merge[row] + merge[kTile + row]) + merge[2 * kTile + row]) + merge[3 * kTile + row];
+                    if (whole) prm.colsum_part[hl + o] = 0.f;
+                }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
             }
         }
     }
@@ -313,14 +389,32 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+// pass 1 epilogue: fold the (at most two) partial row statistics of every query into c_q = m*log2e + log2(l)
+__global__ void pivot_stats_merge_kernel(const float2* __restrict__ ml_part, int H, int L, int Lpad, float* __restrict__ stats) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    const int h = blockIdx.y;
+    if (q >= Lpad) return;
+    const size_t o = (size_t)h * Lpad + q, hl = (size_t)H * Lpad;
+    const float2 p0 = ml_part[o], p1 = ml_part[hl + o];
+    const float mn = fmaxf(p0.x, p1.x);
+    float lt = 0.f;
+    if (p0.x > -INFINITY) lt += p0.y * ex2f((p0.x - mn) * kLog2e);
+    if (p1.x > -INFINITY) lt += p1.y * ex2f((p1.x - mn) * kLog2e);
+    stats[o] = (q < L) ? fmaf(mn, kLog2e, lg2f(lt)) : INFINITY;
+}
+
 // a = bf16(colsum);  head_scores[g] = bf16((sum over the G heads of group g, ATen 4-accumulator order) * f32(1/G))
-__global__ void pivot_head_reduce_kernel(const float* __restrict__ colsum, int H, int G, int L, int Lpad,
+__global__ void pivot_head_reduce_kernel(const float* __restrict__ colsum_part, int H, int G, int L, int Lpad,
                                          __nv_bfloat16* __restrict__ head_scores) {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
     if (k >= L) return;
+    const size_t hl = (size_t)H * Lpad;
     float v[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int j = 0; j < G; ++j) v[j & 3] += round_bf16(colsum[(size_t)(g * G + j) * Lpad + k]);
+    for (int j = 0; j < G; ++j) {
+        const size_t o = (size_t)(g * G + j) * Lpad + k;
+        v[j & 3] += round_bf16(colsum_part[o] + colsum_part[hl + o]);
+    }
     const float s = ((v[0] + v[1]) + v[2]) + v[3];
     head_scores[(size_t)g * L + k] = __float2bfloat16_rn(s * (1.0f / (float)G));
 }
@@ -368,7 +462,7 @@ using namespace rtk;
 extern "C" size_t rtk_pivot_score_workspace_bytes(int64_t H, int64_t L) {
     if (H < 1 || L < 1) return 0;
     const size_t lpad = (size_t)((L + kTile - 1) / kTile) * kTile;
-    return 2 * (size_t)H * lpad * sizeof(float);
+    return 7 * (size_t)H * lpad * sizeof(float);       // ml_part (2 x float2) + stats + colsum_part (2)
 }
 
 extern "C" int rtk_pivot_score(const void* q, int64_t H, int64_t q_stride_h, int64_t q_stride_l, const void* k, int64_t KVH,
@@ -389,8 +483,10 @@ extern "C" int rtk_pivot_score(const void* q, int64_t H, int64_t q_stride_h, int
     prm.n_atoms = (int)(D / 64);
     const float sq = (float)sqrt((double)D);
     prm.inv_sqrt_d = 1.0f / sq;
-    prm.stats = reinterpret_cast<float*>(workspace);
-    prm.colsum = prm.stats + (size_t)H * prm.nt * kTile;
+    const size_t plane = (size_t)H * prm.nt * kTile;
+    prm.ml_part = reinterpret_cast<float2*>(workspace);
+    prm.stats = reinterpret_cast<float*>(workspace) + 4 * plane;
+    prm.colsum_part = prm.stats + plane;
 
     CUtensorMap qm, km;
     int rc = make_map(&qm, q, H, L, D, q_stride_h, q_stride_l, &prm.q_dim1_is_l);
@@ -408,12 +504,15 @@ extern "C" int rtk_pivot_score(const void* q, int64_t H, int64_t q_stride_h, int
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(pivot_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    pivot_score_kernel<1><<<grid, kScoreThreads, smem, st>>>(qm, km, prm);
+    pivot_score_kernel<1><<<grid, kScoreThreads2, smem, st>>>(qm, km, prm);
     RTK_CHECK_LAUNCH();
-    pivot_score_kernel<2><<<grid, kScoreThreads, smem, st>>>(qm, km, prm);
+    dim3 g1((unsigned)((prm.nt * kTile + 255) / 256), (unsigned)H);
+    pivot_stats_merge_kernel<<<g1, 256, 0, st>>>(prm.ml_part, (int)H, (int)L, prm.nt * kTile, prm.stats);
+    RTK_CHECK_LAUNCH();
+    pivot_score_kernel<2><<<grid, kScoreThreads2, smem, st>>>(qm, km, prm);
     RTK_CHECK_LAUNCH();
     dim3 g2((unsigned)((L + 255) / 256), (unsigned)KVH);
-    pivot_head_reduce_kernel<<<g2, 256, 0, st>>>(prm.colsum, (int)H, prm.G, (int)L, prm.nt * kTile,
+    pivot_head_reduce_kernel<<<g2, 256, 0, st>>>(prm.colsum_part, (int)H, prm.G, (int)L, prm.nt * kTile,
                                                  reinterpret_cast<__nv_bfloat16*>(head_scores));
     RTK_CHECK_LAUNCH();
     return 0;
