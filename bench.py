@@ -113,33 +113,27 @@ def synth_host(s, pool, seed):
 
 
 class ScoreTimer:
-    """CUDA-event pairs around a sample of the rtk_pivot_score calls inside the timed region."""
+    """CUDA-event pairs recorded by the library around a sample of the scoring launches (rtk_pivot_score inside
+    rtk_pivot_update) in the timed region; the events live on the stream the kernels are launched on."""
 
     def __init__(self, every=8):
-        self.every, self.n, self.pairs = every, 0, []
-        self.on = False
+        self.every, self.n, self.pairs, self.on = every, 0, [], False
 
-    def install(self, lc):
-        inner = lc.pivot_head_scores
-        timer = self
-
-        def timed(q, k):
-            timer.n += 1
-            if not timer.on or timer.n % timer.every:
-                return inner(q, k)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            out = inner(q, k)
-            b.record()
-            timer.pairs.append((a, b))
-            return out
-        lc.pivot_head_scores = timed
+    def arm(self, cache):
+        self.n += 1
+        if not self.on or self.n % self.every:
+            return
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()                      # forces creation of the underlying cudaEvent_t; re-recorded by the library
+        b.record()
+        cache.score_events = (a.cuda_event, b.cuda_event)
+        self.pairs.append((a, b))
 
     def mean_ms(self):
         return sum(a.elapsed_time(b) for a, b in self.pairs) / max(1, len(self.pairs))
 
 
-def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid):
+def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer=None):
     """one video through the public operators; returns a small device tensor standing for the step's result"""
     out, mask = vc.memory_bank_compress_keyframe(x[None], s.t, 3, sync=False)
     cache = lc.build_kvcache(cache_config(s))
@@ -158,9 +152,12 @@ def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid):
                 pos[0] += cache.get_prev_temporal_idx(layer) + 1
             else:
                 pos[0] += c * (s.L // s.N)
+            if timer is not None:
+                timer.arm(cache)
             cache.update(k[j:j + 1, :Lc].transpose(1, 2), v[j:j + 1, :Lc].transpose(1, 2), layer,
                          {"query_states": q[j:j + 1, :Lc].transpose(1, 2), "position_ids": pos, "rotary_emb": rotary,
                           "mrope_section": s.mrope})
+    cache.after_forward()
     return cache.last_keep_indices, cache.get_seq_length(0)
 
 
@@ -270,7 +267,6 @@ def main():
     from retake import longvideo_cache as lc
     from retake import visual_compression as vc
     timer = ScoreTimer()
-    timer.install(lc)
     rotary = make_rotary(dev)
     host = synth_host(s, a.pool, 1234 + rank)
     x, q, k, v = [h.to(dev, non_blocking=True) for h in host]
@@ -293,7 +289,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        res = run_step(s, x, q, k, v, rotary, lc, vc, pos_grid)
+        res = run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer)
     e1.record()
     sync_all()
     timer.on = False

@@ -127,6 +127,46 @@ int rtk_pivot_compact(const void* k, const void* v, int64_t KVH, int64_t L, int6
                       void* k_out, void* v_out, int64_t out_stride_h,
                       const int64_t* pos, int n_pos, int64_t* pos_out, int reforge, void* stream);
 
+/* cos/sin tables of one chunk from the rotary module's inv_freq (fp32 [D/2]); replaces the two
+ * `rotary_emb_fn(x, position_ids)` calls of longvideo_cache.py:249,298 plus the mrope row selection of :67-73 when
+ * the module is a stock HF rotary embedding with a static inv_freq:
+ *   cos_out/sin_out bf16 [L, D]: bf16(cos(fp32(pos[row(c), l]) * inv_freq[c mod D/2]) * attention_scaling)
+ */
+int rtk_pivot_rope_tables(const int64_t* pos, int n_pos, int64_t L, int64_t D, const float* inv_freq,
+                          const int32_t* mrope_section_host, float attention_scaling, void* cos_out, void* sin_out,
+                          void* stream);
+
+/* One compressing PivotKVCache.update (longvideo_cache.py:244-306) as a single call: un-rotate, score, select,
+ * compact, re-index, re-rotate.  All temporaries live in `workspace` (256-byte aligned). */
+typedef struct rtk_pivot_update_args {
+    const void* q; int64_t H, q_stride_h, q_stride_l;           /* bf16 [H, L, D] view                              */
+    const void* k; int64_t KVH, k_stride_h, k_stride_l;         /* bf16 [KVH, L, D] view                            */
+    const void* v; int64_t v_stride_h, v_stride_l;
+    int64_t k_stride_h_in, k_stride_l_in;                       /* == k_stride_h/l (kept apart: k is re-pointed)    */
+    int64_t L, D;
+    const uint8_t* keymask;                                     /* [L] or NULL                                      */
+    int64_t keep;
+    int32_t reforge;                                            /* pos_embed_reforge                                */
+    int32_t n_pos;                                              /* 3 (mrope) or 1; 0 when pos == NULL               */
+    const int64_t* pos;                                         /* [n_pos, L] or NULL                               */
+    const void* cos; const void* sin;                           /* bf16 [n_pos, L, D] tables, or NULL with inv_freq */
+    const float* inv_freq;                                      /* fp32 [D/2] or NULL                               */
+    float attention_scaling, inv_scale2;                        /* inv_scale2 = fp32(1 / fp32(scaling ** 2))        */
+    int32_t mrope_section[3];
+    int32_t skip_select;                                        /* 1: stop after head_scores (KV-head sharding)     */
+    void* k_out; void* v_out; int64_t out_stride_h;             /* bf16 [KVH, keep, D]                              */
+    int64_t* pos_out;                                           /* [n_pos, keep] or NULL                            */
+    int32_t* keep_idx;                                          /* [keep]                                           */
+    void* head_scores;                                          /* bf16 [KVH, L]                                    */
+    void* workspace; size_t workspace_bytes;
+    void* ev_score_begin; void* ev_score_end;                   /* optional cudaEvent_t pair recorded around the scoring   */
+} rtk_pivot_update_args;
+
+size_t rtk_pivot_update_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D);
+/* With inv_freq the kept keys come back re-rotated; with cos/sin tables (opaque rotary callable) the caller
+ * finishes with rotary_emb_fn(v_out, pos_out) + rtk_pivot_rope(forward=1). */
+int rtk_pivot_update(const rtk_pivot_update_args* args, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -282,3 +282,82 @@ def test_update_full_size_chunk(reforge):
     assert ko.shape[2] == past + 7 and cache.get_seq_length(0) == past + 7
     if reforge:
         assert cache.position_cache[0].shape[-1] == past + 7
+
+
+def _hf_rotary():
+    import bench
+    return bench.make_rotary(torch.device("cuda"))
+
+
+def test_rope_tables_bit_exact_vs_hf_rotary_module():
+    """in-library cos/sin tables == stock HF Qwen2-VL rotary module (YaRN x4) + mrope row selection"""
+    lc = _lc()
+    rot = _hf_rotary()
+    L, D, mrope = 4096, 128, [16, 24, 24]
+    ar = torch.arange(L, device="cuda")
+    for base in (0, 777, 31000):
+        pos = torch.stack([base + ar // 256, (ar % 256) // 16, ar % 16])[:, None]
+        x = torch.zeros(1, 4, L, D, dtype=BF, device="cuda")
+        cos, sin = rot(x, pos)
+        got_c, got_s = lc.pivot_rope_tables(pos, rot.inv_freq, D, mrope, rot.attention_scaling)
+        assert torch.equal(got_c, op.select_mrope(cos, mrope)[0]) and torch.equal(got_s, op.select_mrope(sin, mrope)[0])
+    r1 = TableRotary(64, mrope=False)
+    r1.inv_freq = r1.inv_freq.cuda()
+    pos = (torch.arange(300, device="cuda") * 7 + 3)[None]
+    cos, sin = r1(torch.zeros(1, 2, 300, 64, dtype=BF, device="cuda"), pos)
+    got_c, got_s = lc.pivot_rope_tables(pos, r1.inv_freq, 64, None, r1.attention_scaling)
+    assert torch.equal(got_c, cos[0]) and torch.equal(got_s, sin[0])
+
+
+def test_fused_rotary_path_equals_table_path(monkeypatch):
+    """rtk_pivot_update with inv_freq (tables computed in the library) == calling the rotary module like the reference"""
+    lc = _lc()
+    H, KVH, L, D, mrope = 28, 4, 1024, 128, [16, 24, 24]
+    rot = _hf_rotary()
+    q, k, v = qkv(H, KVH, L, D, 1.0, seed=77)
+    ar = torch.arange(L, device="cuda")
+    pos = torch.stack([5 + ar // 256, (ar % 256) // 16, ar % 16])[:, None]
+    mask = (torch.rand(L, generator=torch.Generator().manual_seed(1)) < 0.2).cuda()
+    res = []
+    for tables in ("0", "1"):
+        monkeypatch.setenv("RTK_ROTARY_TABLES", tables)
+        cache = lc.PivotKVCache(_cfg(H, KVH, D, 1, 0.25, True))
+        cache.keypatches_mask_chunk = mask
+        cache.update(k, v, 0, {"query_states": q, "position_ids": pos.clone(), "rotary_emb": rot, "mrope_section": mrope})
+        res.append((cache.layers[0].keys.clone(), cache.layers[0].values.clone(), cache.position_cache[0].clone(),
+                    cache.last_head_scores.clone(), cache.last_keep_indices.clone()))
+    for a, b in zip(*res):
+        assert torch.equal(a, b)
+
+
+def test_cache_storage_semantics():
+    """in-place append + deferred tail overwrite: what callers can observe"""
+    lc = _lc()
+    H, KVH, L, D = 4, 2, 256, 64
+    cache = lc.PivotKVCache(_cfg(H, KVH, D, 2, 0.5, False))
+    q, k, v = qkv(H, KVH, L, D, 1.0, seed=1)
+    pos = torch.arange(L, device="cuda")[None]
+    ko, vo = cache.update(k, v, 0, {"query_states": q, "position_ids": pos})
+    # the returned views hold the UNcompressed chunk until the next cache operation ...
+    assert torch.equal(ko, k) and torch.equal(vo, v) and cache.get_seq_length(0) == L // 2
+    idx = cache.last_keep_indices.long()
+    # ... which a read of the cache itself is: it sees [kept]
+    assert torch.equal(cache.key_cache[0], k[:, :, idx]) and torch.equal(cache.layers[0].values, v[:, :, idx])
+    assert cache.key_cache[0].shape[2] == L // 2
+    # second chunk: past = kept rows of chunk 1, returned view = [kept | chunk 2]
+    q2, k2, v2 = qkv(H, KVH, L, D, 1.0, seed=2)
+    ko2, vo2 = cache.update(k2, v2, 0, {"query_states": q2, "position_ids": pos + L})
+    assert ko2.shape[2] == L // 2 + L and torch.equal(ko2[:, :, :L // 2], k[:, :, idx]) and torch.equal(ko2[:, :, L // 2:], k2)
+    # another layer's update settles layer 0 (its attention is already on the stream in a real forward)
+    cache.update(k, v, 1, {"query_states": q, "position_ids": pos})
+    idx2 = cache.last_keep_indices
+    assert cache.layers[0]._pending is None and cache.get_seq_length(0) == L and cache.get_seq_length(1) == L // 2
+    # 4.48-style assignment and DynamicCache housekeeping still work
+    cache.key_cache[0] = cache.key_cache[0][:, :, :10].clone()
+    cache.value_cache[0] = cache.value_cache[0][:, :, :10].clone()
+    assert cache.get_seq_length(0) == 10
+    cache.kvcache_compression = False
+    ko3, _ = cache.update(k[:, :, :3], v[:, :, :3], 0, {"position_ids": pos[:, :3]})
+    assert ko3.shape[2] == 13 and cache.get_seq_length(0) == 13
+    cache.after_forward()
+    assert cache.num_evicted_tokens == [L, L // 2]

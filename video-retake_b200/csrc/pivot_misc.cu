@@ -21,6 +21,24 @@ __device__ __forceinline__ int rope_pos_row(const RopeParams& p, int c) {
     return i % 3;
 }
 
+// cos/sin tables of one chunk straight from the rotary module's inv_freq: what HF's rotary forward computes
+// (freqs = inv_freq * pos in fp32, emb = cat(freqs, freqs), cos(emb) * attention_scaling -> bf16), already
+// reduced to the one position row each channel uses under mrope.  Replaces ~12 small torch launches per call.
+__global__ void __launch_bounds__(256)
+pivot_rope_table_kernel(const long long* __restrict__ pos, const float* __restrict__ inv_freq, RopeParams p, float scaling,
+                        __nv_bfloat16* __restrict__ cos_t, __nv_bfloat16* __restrict__ sin_t) {
+    const int half = p.D >> 1;
+    const long long total = (long long)p.L * p.D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % p.D);
+        const int l = (int)(i / p.D);
+        const long long pv = pos[(size_t)rope_pos_row(p, c) * p.L + l];
+        const float ang = inv_freq[c < half ? c : c - half] * (float)pv;
+        cos_t[i] = __float2bfloat16_rn(cosf(ang) * scaling);
+        sin_t[i] = __float2bfloat16_rn(sinf(ang) * scaling);
+    }
+}
+
 // one thread: 8 channels of the lower half and the 8 partner channels of the upper half of one (head, token)
 __global__ void __launch_bounds__(256)
 pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ cos_t,
@@ -198,10 +216,8 @@ pivot_compact_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* _
         const int h = (int)(hj / p.keep);
         const size_t so = (size_t)h * p.stride_h + (size_t)keep_idx[j] * p.stride_l + (size_t)c * 8;
         const size_t dof = (size_t)h * p.out_stride_h + (size_t)j * p.D + (size_t)c * 8;
-        const uint4 kv = __ldg(reinterpret_cast<const uint4*>(k + so));
-        const uint4 vv = __ldg(reinterpret_cast<const uint4*>(v + so));
-        *reinterpret_cast<uint4*>(k_out + dof) = kv;
-        *reinterpret_cast<uint4*>(v_out + dof) = vv;
+        if (k) *reinterpret_cast<uint4*>(k_out + dof) = __ldg(reinterpret_cast<const uint4*>(k + so));
+        if (v) *reinterpret_cast<uint4*>(v_out + dof) = __ldg(reinterpret_cast<const uint4*>(v + so));
     }
 }
 
@@ -273,10 +289,11 @@ extern "C" int rtk_pivot_compact(const void* k, const void* v, int64_t KVH, int6
                                  int64_t stride_l, const int32_t* keep_idx, int64_t keep, void* k_out, void* v_out,
                                  int64_t out_stride_h, const int64_t* pos, int n_pos, int64_t* pos_out, int reforge,
                                  void* stream) {
-    if (!k || !v || !keep_idx || !k_out || !v_out || KVH < 1 || L < 1 || D < 8 || keep < 1 || keep > L) return RTK_E_BADARG;
+    if ((!k && !v) || !keep_idx || (k && !k_out) || (v && !v_out) || KVH < 1 || L < 1 || D < 8 || keep < 1 || keep > L)
+        return RTK_E_BADARG;
     if (pos && (!pos_out || n_pos < 1)) return RTK_E_BADARG;
     if (D % 8 != 0) return RTK_E_UNSUPPORTED;
-    if ((((uintptr_t)k | (uintptr_t)v | (uintptr_t)k_out | (uintptr_t)v_out) & 15u) != 0) return RTK_E_ALIGN;
+    if ((((uintptr_t)k | (uintptr_t)v | (uintptr_t)k_out | (uintptr_t)v_out) & 15u) != 0) return RTK_E_ALIGN;   // NULL passes
     if ((stride_h | stride_l | out_stride_h) % 8 != 0) return RTK_E_ALIGN;
     CompactParams p;
     p.KVH = (int)KVH; p.L = (int)L; p.D = (int)D; p.keep = (int)keep; p.n_pos = n_pos; p.reforge = reforge;
@@ -289,5 +306,105 @@ extern "C" int rtk_pivot_compact(const void* k, const void* v, int64_t KVH, int6
         (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, keep_idx, (__nv_bfloat16*)k_out, (__nv_bfloat16*)v_out,
         (const long long*)pos, (long long*)pos_out, p);
     RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rtk_pivot_rope_tables(const int64_t* pos, int n_pos, int64_t L, int64_t D, const float* inv_freq,
+                                     const int32_t* mrope_section_host, float attention_scaling, void* cos_out,
+                                     void* sin_out, void* stream) {
+    if (!pos || !inv_freq || !cos_out || !sin_out || L < 1 || D < 2) return RTK_E_BADARG;
+    if (D % 2 != 0 || (n_pos != 1 && n_pos != 3)) return RTK_E_UNSUPPORTED;
+    if (n_pos == 3 && !mrope_section_host) return RTK_E_BADARG;
+    RopeParams p;
+    p.heads = 1; p.L = (int)L; p.D = (int)D; p.n_pos = n_pos; p.forward = 0;
+    p.stride_h = p.stride_l = p.out_stride_h = p.out_stride_l = 0;
+    p.inv_scale2 = 1.0f;
+    int acc = 0;
+    for (int i = 0; i < 6; ++i) {
+        acc += (n_pos == 3) ? mrope_section_host[i % 3] : 0;
+        p.bound[i] = acc;
+    }
+    if (n_pos == 3 && acc != D) return RTK_E_UNSUPPORTED;
+    long long grid = (L * D + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    pivot_rope_table_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)pos, inv_freq, p, attention_scaling, (__nv_bfloat16*)cos_out, (__nv_bfloat16*)sin_out);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" size_t rtk_pivot_update_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D) {
+    if (H < 1 || KVH < 1 || L < 1 || D < 1) return 0;
+    return align256(rtk_pivot_score_workspace_bytes(H, L)) + align256((size_t)H * L * D * 2) + align256((size_t)KVH * L * D * 2) +
+           4 * align256((size_t)L * D * 2);
+}
+
+extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
+    if (!a || !a->q || !a->k || !a->v || !a->k_out || !a->v_out || !a->keep_idx || !a->head_scores || !a->workspace)
+        return RTK_E_BADARG;
+    if (a->workspace_bytes < rtk_pivot_update_workspace_bytes(a->H, a->KVH, a->L, a->D)) return RTK_E_WORKSPACE;
+    if (((uintptr_t)a->workspace & 255u) != 0) return RTK_E_ALIGN;
+    const int64_t H = a->H, KVH = a->KVH, L = a->L, D = a->D;
+    char* ws = (char*)a->workspace;
+    void* score_ws = ws;                ws += align256(rtk_pivot_score_workspace_bytes(H, L));
+    void* qu = ws;                      ws += align256((size_t)H * L * D * 2);
+    void* ku = ws;                      ws += align256((size_t)KVH * L * D * 2);
+    void* cos1 = ws;                    ws += align256((size_t)L * D * 2);
+    void* sin1 = ws;                    ws += align256((size_t)L * D * 2);
+    void* cos2 = ws;                    ws += align256((size_t)L * D * 2);
+    void* sin2 = ws;
+    const void* q = a->q;
+    const void* k = a->k;
+    int64_t qsh = a->q_stride_h, qsl = a->q_stride_l, ksh = a->k_stride_h, ksl = a->k_stride_l;
+    int rc;
+    const bool fused_tables = a->reforge && a->inv_freq;
+    if (a->reforge) {
+        if (!a->pos || !a->pos_out) return RTK_E_BADARG;
+        const void *c = a->cos, *s = a->sin;
+        int n_pos_tab = a->n_pos;
+        const int32_t* sec = a->n_pos == 3 ? a->mrope_section : nullptr;
+        if (fused_tables) {
+            rc = rtk_pivot_rope_tables(a->pos, a->n_pos, L, D, a->inv_freq, sec, a->attention_scaling, cos1, sin1, stream);
+            if (rc) return rc;
+            c = cos1; s = sin1; n_pos_tab = 1; sec = nullptr;
+        } else if (!c || !s) {
+            return RTK_E_BADARG;
+        }
+        rc = rtk_pivot_rope(q, H, L, D, qsh, qsl, c, s, n_pos_tab, sec, a->inv_scale2, 0, qu, L * D, D, stream);
+        if (rc) return rc;
+        rc = rtk_pivot_rope(k, KVH, L, D, ksh, ksl, c, s, n_pos_tab, sec, a->inv_scale2, 0, ku, L * D, D, stream);
+        if (rc) return rc;
+        q = qu; k = ku; qsh = ksh = L * D; qsl = ksl = D;
+    }
+    if (a->ev_score_begin) cudaEventRecord((cudaEvent_t)a->ev_score_begin, (cudaStream_t)stream);
+    rc = rtk_pivot_score(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, a->head_scores, score_ws, rtk_pivot_score_workspace_bytes(H, L), stream);
+    if (rc) return rc;
+    if (a->ev_score_end) cudaEventRecord((cudaEvent_t)a->ev_score_end, (cudaStream_t)stream);
+    if (a->skip_select) return 0;
+    rc = rtk_pivot_select(a->head_scores, KVH, L, a->keymask, a->keep, a->keep_idx, nullptr, stream);
+    if (rc) return rc;
+    if (!a->reforge && a->v_stride_h == a->k_stride_h_in && a->v_stride_l == a->k_stride_l_in) {
+        rc = rtk_pivot_compact(k, a->v, KVH, L, D, ksh, ksl, a->keep_idx, a->keep, a->k_out, a->v_out, a->out_stride_h, a->pos,
+                               a->pos ? a->n_pos : 0, a->pos_out, 0, stream);
+        if (rc) return rc;
+    } else {
+        // K comes from the un-rotated copy (or has other strides than V): gather K + positions, then V alone
+        rc = rtk_pivot_compact(k, nullptr, KVH, L, D, ksh, ksl, a->keep_idx, a->keep, a->k_out, nullptr, a->out_stride_h, a->pos,
+                               a->pos ? a->n_pos : 0, a->pos_out, a->reforge, stream);
+        if (rc) return rc;
+        rc = rtk_pivot_compact(nullptr, a->v, KVH, L, D, a->v_stride_h, a->v_stride_l, a->keep_idx, a->keep, nullptr, a->v_out,
+                               a->out_stride_h, nullptr, 0, nullptr, 0, stream);
+        if (rc) return rc;
+    }
+    if (fused_tables) {
+        const int32_t* sec = a->n_pos == 3 ? a->mrope_section : nullptr;
+        rc = rtk_pivot_rope_tables(a->pos_out, a->n_pos, a->keep, D, a->inv_freq, sec, a->attention_scaling, cos2, sin2, stream);
+        if (rc) return rc;
+        rc = rtk_pivot_rope(a->k_out, KVH, a->keep, D, a->out_stride_h, D, cos2, sin2, 1, nullptr, 1.0f, 1, a->k_out,
+                            a->out_stride_h, D, stream);
+        if (rc) return rc;
+    }
     return 0;
 }

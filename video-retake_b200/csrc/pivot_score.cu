@@ -74,6 +74,32 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+// wait for the outstanding TMEM loads; the registers are listed so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+// acc(fp32) += one half of a packed bf16x2 (SASS FHADD.BF16, no unpack needed)
+__device__ __forceinline__ void add_bf16_pair(float& acc_lo, float& acc_hi, uint32_t packed) {
+    asm("{\n\t.reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %2;\n\t"
+        "add.rn.f32.bf16 %0, lo, %0;\n\t"
+        "add.rn.f32.bf16 %1, hi, %1;\n\t}"
+        : "+f"(acc_lo), "+f"(acc_hi)
+        : "r"(packed));
+}
 
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
@@ -292,7 +318,8 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
         while (range.next(u, tb0, tb1)) {
             const int h = u / nt, ta = u - h * nt;
             float m = -INFINITY;                 // pass 1: running max (scaled-logit domain)
-            uint64_t acc = pk2(0.f, 0.f);        // pass 1: row sum, pass 2: column sum (two interleaved halves)
+            uint64_t acc = pk2(0.f, 0.f);        // pass 1: row sum (two interleaved halves)
+            float c0 = 0.f, c1 = 0.f;            // pass 2: column sum (two interleaved halves)
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 if ((int)(cnt & 1u) != (grp >> 1)) continue;
                 const int b = cnt % kAccBufs;
@@ -301,48 +328,54 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
                 const int valid = prm.L - tb * kTile - half * 64;      // streamed rows of this half that exist
                 const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + half * 64;
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    uint32_t r[32];
-                    tmem_ld32(lane_addr + b * kTile + c * 32, r);
-                    tmem_ld_wait();
+                const uint32_t taddr = lane_addr + b * kTile;
+                // 64 columns in four 16-column steps; the TMEM load of step j+1 is in flight while step j is computed
+                uint32_t ra[16], rb[16];
+                tmem_ld16(taddr, ra);
+                tmem_ld_wait16(ra);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t (&r)[16] = (j & 1) ? rb : ra;
+                    uint32_t (&rn)[16] = (j & 1) ? ra : rb;
+                    if (j < 3) tmem_ld16(taddr + (j + 1) * 16, rn);
                     if (PASS == 1) {
                         if (valid < 64) {
 #pragma unroll
-                            for (int i = 0; i < 32; ++i)
-                                if (c * 32 + i >= valid) r[i] = 0xff800000u;     // -inf: padded key column
+                            for (int i = 0; i < 16; ++i)
+                                if (j * 16 + i >= valid) r[i] = 0xff800000u;     // -inf: padded key column
                         }
                         // the rounding chain is monotone, so the row max of the rounded logits is the chain of the raw max
                         float mx = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
 #pragma unroll
-                        for (int i = 3; i < 31; i += 2)
+                        for (int i = 3; i < 15; i += 2)
                             mx = fmaxf(fmaxf(mx, __uint_as_float(r[i])), __uint_as_float(r[i + 1]));
-                        mx = fmaxf(mx, __uint_as_float(r[31]));
+                        mx = fmaxf(mx, __uint_as_float(r[15]));
                         const float mn = fmaxf(m, logit_chain1(mx, inv));
-                        if (mn > -INFINITY) {
-                            const float mm = mn * kLog2e;
-                            const float sc = ex2f(fmaf(m, kLog2e, -mm));           // m == -inf -> 0
+                        if (__any_sync(0xffffffffu, mn > m)) {                     // rare after the first few steps
+                            const float sc = (mn > -INFINITY) ? ex2f((m - mn) * kLog2e) : 0.f;   // m == -inf -> 0
                             acc = mul2(acc, pk2(sc, sc));
-                            const uint64_t nmm = pk2(-mm, -mm);
-#pragma unroll
-                            for (int i = 0; i < 32; i += 2) {
-                                float y0, y1;
-                                upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), y0, y1);
-                                acc = add2(acc, pk2(ex2f(y0), ex2f(y1)));
-                            }
                             m = mn;
+                        }
+                        const float mm = (m > -INFINITY) ? m * kLog2e : 0.f;
+                        const uint64_t nmm = pk2(-mm, -mm);
+#pragma unroll
+                        for (int i = 0; i < 16; i += 2) {
+                            float y0, y1;
+                            upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), y0, y1);
+                            acc = add2(acc, pk2(ex2f(y0), ex2f(y1)));
                         }
                     } else {
 #pragma unroll
-                        for (int i = 0; i < 32; i += 4) {
-                            const float4 cc = *reinterpret_cast<const float4*>(cq + c * 32 + i);
+                        for (int i = 0; i < 16; i += 4) {
+                            const float4 cc = *reinterpret_cast<const float4*>(cq + j * 16 + i);
                             float y0, y1, y2, y3;
                             upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y)), y0, y1);
                             upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w)), y2, y3);
-                            acc = add2(acc, widen2(pack_bf16x2_rn(ex2f(y0), ex2f(y1))));
-                            acc = add2(acc, widen2(pack_bf16x2_rn(ex2f(y2), ex2f(y3))));
+                            add_bf16_pair(c0, c1, pack_bf16x2_rn(ex2f(y0), ex2f(y1)));
+                            add_bf16_pair(c0, c1, pack_bf16x2_rn(ex2f(y2), ex2f(y3)));
                         }
                     }
+                    if (j < 3) tmem_ld_wait16(rn);
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -351,6 +384,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
             // ---- fold the four groups and write this CTA's share of the unit
             float a0, a1;
             upk2(acc, a0, a1);
+            if (PASS == 2) { a0 = c0; a1 = c1; }
             const int part = (tb0 == 0) ? 0 : 1;
             const bool whole = (tb0 == 0) && (tb1 == nt);
             const size_t o = (size_t)h * nt * kTile + (size_t)ta * kTile + row;

@@ -43,6 +43,9 @@ def lib() -> C.CDLL:
         "rtk_pivot_score": ([p, i64, i64, i64, p, i64, i64, i64, i64, i64, p, p, sz, p], C.c_int),
         "rtk_pivot_select": ([p, i64, i64, p, i64, p, p, p], C.c_int),
         "rtk_pivot_compact": ([p, p, i64, i64, i64, i64, i64, p, i64, p, p, i64, p, i32, p, i32, p], C.c_int),
+        "rtk_pivot_rope_tables": ([p, i32, i64, i64, p, p, f32, p, p, p], C.c_int),
+        "rtk_pivot_update_workspace_bytes": ([i64, i64, i64, i64], sz),
+        "rtk_pivot_update": ([p, p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)            # AttributeError here == header and library disagree
@@ -55,7 +58,8 @@ def lib() -> C.CDLL:
 
 EXPORTS = ("rtk_version", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
            "rtk_dpselect_gather", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
-           "rtk_pivot_select", "rtk_pivot_compact")
+           "rtk_pivot_select", "rtk_pivot_compact", "rtk_pivot_rope_tables", "rtk_pivot_update_workspace_bytes",
+           "rtk_pivot_update")
 
 
 def check(rc: int, what: str) -> None:

@@ -3,27 +3,32 @@
 ``PivotKVCache`` / ``build_kvcache`` keep the reference's names, constructor, mutable attributes
 (``kvcache_compression``, ``keypatches_mask_chunk``, ``pos_embed_reforge``), hooks (``before_forward`` /
 ``after_forward``), accessors and the ``update(key, value, layer_idx, cache_kwargs)`` contract
-(``longvideo_cache.py:119-334``).  What ``update`` does when compression is on is five kernel launches
-through the C ABI (``include/rtk_b200.h``) on the current stream instead of ~40 torch ops and three L x L
-temporaries:
+(``longvideo_cache.py:119-334``).  A compressing ``update`` is ONE call into the C ABI
+(``rtk_pivot_update``, ``include/rtk_b200.h``) that enqueues, on the current stream and without any host
+synchronisation, what the reference does with ~40 torch ops and three L x L temporaries:
 
-    rtk_pivot_rope (x2, reforge only)  un-rotate q and k                       (reference lines 248-259)
-    rtk_pivot_score                    tcgen05 Q.K^T + softmax + column sums   (lines 260-269)
-    rtk_pivot_select                   KV-head mean, key-patch fill, top-k     (lines 270-277)
-    rtk_pivot_compact                  K/V/position gather, temporal re-index  (lines 278-295)
-    rtk_pivot_rope (forward, reforge)  re-rotate the kept keys                 (lines 297-306)
+    rope tables + un-rotation of q, k (reforge)   reference lines 248-259
+    tcgen05 Q.K^T + softmax + column sums         lines 260-269
+    KV-head mean, key-patch fill, top-k           lines 270-277
+    K / V / position gather, temporal re-index    lines 278-295
+    re-rotation of the kept keys                  lines 297-306
 
-The cache object is a ``transformers.DynamicCache`` (5.x layout: ``layers[i].keys/.values``);
-``key_cache`` / ``value_cache`` are kept as list views for code written against 4.48.
+Storage differs from ``DynamicCache`` (which re-``cat``s the whole past twice per layer and chunk,
+``longvideo_cache.py:238,313-318``): every layer owns a geometrically grown buffer; a chunk is appended in
+place, ``update`` returns views ``[past | chunk]``, and the kept rows are written over the chunk's head only when
+the next cache operation comes in (``update`` of any layer, ``after_forward``, or a read of ``layers[i].keys`` /
+``key_cache[i]``) - i.e. after this layer's attention has been enqueued on the stream, because that attention
+still needs the uncompressed chunk (``longvideo_cache.py:237,323``).  Single stream, as in the reference.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
 import torch
-from transformers.cache_utils import DynamicCache
+from transformers.cache_utils import Cache, DynamicCache, DynamicLayer
 from transformers.utils import logging
 
 from . import _native as N
@@ -31,7 +36,7 @@ from . import _native as N
 logger = logging.get_logger(__name__)
 
 __all__ = ["PivotKVCache", "build_kvcache", "repeat_kv", "rotate_half", "pivot_head_scores", "pivot_select",
-           "pivot_compact", "pivot_rope"]
+           "pivot_compact", "pivot_rope", "pivot_rope_tables"]
 
 
 # ----------------------------------------------------------------------------------------- thin kernel wrappers
@@ -48,8 +53,7 @@ def _hld(x: torch.Tensor, name: str):
 _WS: Dict[Any, torch.Tensor] = {}
 
 
-def _workspace(device, H: int, L: int) -> torch.Tensor:
-    need = int(N.lib().rtk_pivot_score_workspace_bytes(H, L))
+def _workspace(device, need: int) -> torch.Tensor:
     key = (device.index if device.index is not None else torch.cuda.current_device())
     ws = _WS.get(key)
     if ws is None or ws.numel() < need:
@@ -58,25 +62,51 @@ def _workspace(device, H: int, L: int) -> torch.Tensor:
     return ws
 
 
+def _sections(mrope_section):
+    return (C.c_int32 * 3)(*[int(s) for s in mrope_section]) if mrope_section else None
+
+
+def _inv_scale2(attention_scaling: float) -> float:
+    # ATen-CUDA divides a bf16 tensor by a python float as x * fp32(1 / fp32(d))
+    return float(np.float32(1.0) / np.float32(float(attention_scaling) ** 2))
+
+
 def pivot_rope(x: torch.Tensor, cos: torch.Tensor, sin: torch.Tensor, mrope_section, attention_scaling: float = 1.0,
                forward: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """(Un-)rotate ``x[1, heads, L, D]`` with the rotary tables returned by the model's ``rotary_emb``."""
+    """(Un-)rotate ``x[1, heads, L, D]`` with the rotary tables returned by the model's ``rotary_emb``
+    (``[3, 1, L, D]`` with ``mrope_section``, else ``[1, L, D]``; an already selected ``[L, D]`` table also works)."""
     x, heads, L, D, sh, sl = _hld(x, "x")
-    n_pos = 3 if mrope_section else 1
     cos = cos.contiguous()
     sin = sin.contiguous()
+    n_pos = 3 if (mrope_section and cos.numel() == 3 * L * D) else 1
     if cos.numel() != n_pos * L * D or cos.dtype != torch.bfloat16:
         raise ValueError("cos/sin must be bf16 [n_pos, 1, L, D] tables for this chunk")
     if out is None:
         out = torch.empty((1, heads, L, D), dtype=x.dtype, device=x.device)
-    sec = (C.c_int32 * 3)(*[int(s) for s in mrope_section]) if mrope_section else None
-    s2 = np.float32(float(attention_scaling) ** 2)
-    inv = float(np.float32(1.0) / s2)
     with torch.cuda.device(x.device):
-        N.check(N.lib().rtk_pivot_rope(x.data_ptr(), heads, L, D, sh, sl, cos.data_ptr(), sin.data_ptr(), n_pos, sec,
-                                       inv, int(forward), out.data_ptr(), out.stride(1), out.stride(2),
+        N.check(N.lib().rtk_pivot_rope(x.data_ptr(), heads, L, D, sh, sl, cos.data_ptr(), sin.data_ptr(), n_pos,
+                                       _sections(mrope_section) if n_pos == 3 else None, _inv_scale2(attention_scaling),
+                                       int(forward), out.data_ptr(), out.stride(1), out.stride(2),
                                        N.stream_ptr(x.device)), "rtk_pivot_rope")
     return out
+
+
+def pivot_rope_tables(position_ids: torch.Tensor, inv_freq: torch.Tensor, head_dim: int, mrope_section,
+                      attention_scaling: float):
+    """bf16 ``[L, D]`` cos/sin tables for ``position_ids`` (``[3, 1, L]`` with mrope, else ``[1, L]``)."""
+    N.require_cuda(position_ids, "position_ids", torch.int64)
+    L = position_ids.shape[-1]
+    pos = position_ids.reshape(-1, L).contiguous()
+    n_pos = pos.shape[0]
+    inv = inv_freq.to(device=pos.device, dtype=torch.float32).contiguous()
+    cos = torch.empty((L, head_dim), dtype=torch.bfloat16, device=pos.device)
+    sin = torch.empty_like(cos)
+    with torch.cuda.device(pos.device):
+        N.check(N.lib().rtk_pivot_rope_tables(pos.data_ptr(), n_pos, L, head_dim, inv.data_ptr(),
+                                              _sections(mrope_section) if n_pos == 3 else None, float(attention_scaling),
+                                              cos.data_ptr(), sin.data_ptr(), N.stream_ptr(pos.device)),
+                "rtk_pivot_rope_tables")
+    return cos, sin
 
 
 def pivot_head_scores(query_states: torch.Tensor, key_states: torch.Tensor) -> torch.Tensor:
@@ -86,7 +116,7 @@ def pivot_head_scores(query_states: torch.Tensor, key_states: torch.Tensor) -> t
     if Lk != L or Dk != D:
         raise ValueError("PivotKV scores the chunk's own keys: key and query lengths must match")
     hs = torch.empty((KVH, L), dtype=torch.bfloat16, device=q.device)
-    ws = _workspace(q.device, H, L)
+    ws = _workspace(q.device, int(N.lib().rtk_pivot_update_workspace_bytes(H, KVH, L, D)))
     with torch.cuda.device(q.device):
         N.check(N.lib().rtk_pivot_score(q.data_ptr(), H, qsh, qsl, k.data_ptr(), KVH, ksh, ksl, L, D, hs.data_ptr(),
                                         ws.data_ptr(), ws.numel(), N.stream_ptr(q.device)), "rtk_pivot_score")
@@ -142,6 +172,41 @@ def pivot_compact(key_states: torch.Tensor, value_states: torch.Tensor, keep_idx
     return k_out, v_out, pos_out
 
 
+class _UpdateArgs(C.Structure):
+    """mirror of ``rtk_pivot_update_args`` (include/rtk_b200.h)"""
+    _fields_ = [("q", C.c_void_p), ("H", C.c_int64), ("q_stride_h", C.c_int64), ("q_stride_l", C.c_int64),
+                ("k", C.c_void_p), ("KVH", C.c_int64), ("k_stride_h", C.c_int64), ("k_stride_l", C.c_int64),
+                ("v", C.c_void_p), ("v_stride_h", C.c_int64), ("v_stride_l", C.c_int64),
+                ("k_stride_h_in", C.c_int64), ("k_stride_l_in", C.c_int64),
+                ("L", C.c_int64), ("D", C.c_int64),
+                ("keymask", C.c_void_p), ("keep", C.c_int64),
+                ("reforge", C.c_int32), ("n_pos", C.c_int32),
+                ("pos", C.c_void_p), ("cos", C.c_void_p), ("sin", C.c_void_p), ("inv_freq", C.c_void_p),
+                ("attention_scaling", C.c_float), ("inv_scale2", C.c_float),
+                ("mrope_section", C.c_int32 * 3), ("skip_select", C.c_int32),
+                ("k_out", C.c_void_p), ("v_out", C.c_void_p), ("out_stride_h", C.c_int64),
+                ("pos_out", C.c_void_p), ("keep_idx", C.c_void_p), ("head_scores", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("ev_score_begin", C.c_void_p), ("ev_score_end", C.c_void_p)]
+
+
+_STATIC_INV_FREQ_ROPE = ("default", "yarn", "linear", "llama3")
+
+
+def _rotary_inv_freq(rotary):
+    """(inv_freq fp32 tensor, attention_scaling) when ``rotary`` is a stock rotary module with a static inv_freq
+    (the tables are then computed inside the library), else None (the module is called like the reference does)."""
+    if os.environ.get("RTK_ROTARY_TABLES") == "1":
+        return None
+    inv = getattr(rotary, "inv_freq", None)
+    sc = getattr(rotary, "attention_scaling", None)
+    if not isinstance(inv, torch.Tensor) or sc is None or inv.dim() != 1:
+        return None
+    if getattr(rotary, "rope_type", "default") not in _STATIC_INV_FREQ_ROPE:
+        return None
+    return inv, float(sc)
+
+
 # ------------------------------------------------------------------------- helpers kept for API compatibility
 def repeat_kv(hidden_states: torch.Tensor, n_rep: int) -> torch.Tensor:
     """(batch, kv_heads, L, D) -> (batch, kv_heads * n_rep, L, D); the kernels index GQA groups instead."""
@@ -154,6 +219,105 @@ def repeat_kv(hidden_states: torch.Tensor, n_rep: int) -> torch.Tensor:
 def rotate_half(x: torch.Tensor) -> torch.Tensor:
     h = x.shape[-1] // 2
     return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+
+class PivotKVLayer(DynamicLayer):
+    """One layer's K/V in a geometrically grown buffer ``[1, KVH, cap, D]`` with in-place append and a deferred
+    overwrite of the last chunk by its kept rows.  ``keys`` / ``values`` are views of the valid prefix."""
+
+    def __init__(self):
+        super().__init__()
+        self._kbuf = self._vbuf = None
+        self._len = 0
+        self._pending = None            # (kept_k, kept_v, start) waiting to be written at [start, start + keep)
+
+    # -- HF reads these attributes; a read settles the deferred write first
+    @property
+    def keys(self):
+        self.flush()
+        return self._keys_view
+
+    @keys.setter
+    def keys(self, t):
+        self._adopt(t, "k")
+
+    @property
+    def values(self):
+        self.flush()
+        return self._values_view
+
+    @values.setter
+    def values(self, t):
+        self._adopt(t, "v")
+
+    def _adopt(self, t, which):
+        # external assignment (4.48-style ``cache.key_cache[i] = tensor``, crop, reorder ...): take it as the buffer
+        if t is None or not isinstance(t, torch.Tensor) or t.numel() == 0:
+            if which == "k":
+                self._kbuf, self._keys_view, self._len = None, t, 0
+            else:
+                self._vbuf, self._values_view = None, t
+            self._pending = None
+            return
+        self.flush()
+        t = t if t.is_contiguous() else t.contiguous()
+        if which == "k":
+            self._kbuf, self._keys_view, self._len = t, t, t.shape[-2]
+        else:
+            self._vbuf, self._values_view = t, t
+
+    def lazy_initialization(self, key_states, value_states=None):
+        self.dtype, self.device = key_states.dtype, key_states.device
+        self._keys_view = torch.tensor([], dtype=self.dtype, device=self.device)
+        self._values_view = torch.tensor([], dtype=self.dtype, device=self.device)
+        self.is_initialized = True
+
+    def get_seq_length(self) -> int:
+        return self._len if self.is_initialized else 0
+
+    def flush(self):
+        p = self._pending
+        if p is not None:
+            self._pending = None
+            kk, vv, start = p
+            n = kk.shape[2]
+            self._kbuf[:, :, start:start + n].copy_(kk)
+            self._vbuf[:, :, start:start + n].copy_(vv)
+
+    def _reserve(self, heads, n, d):
+        cap = 0 if self._kbuf is None else self._kbuf.shape[2]
+        if n <= cap and self._vbuf is not None and self._vbuf.shape[2] >= n:
+            return
+        new_cap = max(n, int(cap * 1.5), 8192)
+        kb = torch.empty((1, heads, new_cap, d), dtype=self.dtype, device=self.device)
+        vb = torch.empty_like(kb)
+        if self._len:
+            kb[:, :, :self._len].copy_(self._kbuf[:, :, :self._len])
+            vb[:, :, :self._len].copy_(self._vbuf[:, :, :self._len])
+        self._kbuf, self._vbuf = kb, vb
+
+    def update(self, key_states, value_states, *args, **kwargs):
+        """append in place, return views ``[past | new]``"""
+        if not self.is_initialized:
+            self.lazy_initialization(key_states, value_states)
+        self.flush()
+        _, heads, n_new, d = key_states.shape
+        p = self._len
+        self._reserve(heads, p + n_new, d)
+        self._kbuf[:, :, p:p + n_new].copy_(key_states)
+        self._vbuf[:, :, p:p + n_new].copy_(value_states)
+        self._len = p + n_new
+        self._keys_view = self._kbuf[:, :, :self._len]
+        self._values_view = self._vbuf[:, :, :self._len]
+        return self._keys_view, self._values_view
+
+    def replace_tail(self, n_tail, kept_k, kept_v):
+        """the last ``n_tail`` rows become ``kept_*`` - length changes now, bytes move at the next flush"""
+        start = self._len - n_tail
+        self._pending = (kept_k, kept_v, start)
+        self._len = start + kept_k.shape[2]
+        self._keys_view = self._kbuf[:, :, :self._len]
+        self._values_view = self._vbuf[:, :, :self._len]
 
 
 class _LayerListView:
@@ -177,7 +341,7 @@ class _LayerListView:
 
 class PivotKVCache(DynamicCache):
     def __init__(self, config) -> None:
-        super().__init__()
+        Cache.__init__(self, layer_class_to_replicate=PivotKVLayer)
         self.config = config
         llm_config = config.text_config if hasattr(config, "text_config") else config   # LLaVA-OneVision / Qwen2-VL
         self.hidden_size = llm_config.hidden_size
@@ -196,7 +360,11 @@ class PivotKVCache(DynamicCache):
         self.position_cache: List[torch.Tensor] = []
         self.num_evicted_tokens: List[int] = []
         self.keypatches_mask_chunk: Optional[torch.Tensor] = None
-        # exposed for tests / the multi-GPU path: last chunk's per-KV-head scores and kept indices
+        self._pos_buf: List[Optional[torch.Tensor]] = []
+        self._pos_len: List[int] = []
+        self._dirty: List[PivotKVLayer] = []
+        self.score_events = None            # optional (cudaEvent_t, cudaEvent_t) ints recorded around the next scoring
+        # exposed for tests / the multi-GPU path: the last chunk's per-KV-head scores and kept indices
         self.last_head_scores: Optional[torch.Tensor] = None
         self.last_keep_indices: Optional[torch.Tensor] = None
 
@@ -213,7 +381,13 @@ class PivotKVCache(DynamicCache):
         pass
 
     def after_forward(self, **kwargs):
-        pass
+        self.flush()
+
+    def flush(self):
+        """settle every deferred tail overwrite (cheap no-op when nothing is pending)"""
+        dirty, self._dirty = self._dirty, []
+        for layer in dirty:
+            layer.flush()
 
     def update_num_evicted_tokens(self, num_tokens: int, layer_idx: int) -> int:
         while len(self.num_evicted_tokens) <= layer_idx:
@@ -222,25 +396,104 @@ class PivotKVCache(DynamicCache):
         return self.num_evicted_tokens[layer_idx]
 
     def update_position_ids(self, position_ids: torch.Tensor, layer_idx: int) -> torch.Tensor:
-        while len(self.position_cache) < layer_idx:
+        """append along the last dim into a grown buffer; ``position_cache[layer_idx]`` is the valid view"""
+        while len(self.position_cache) <= layer_idx:
             self.position_cache.append([])
-        if len(self.position_cache) == layer_idx:
-            self.position_cache.append(position_ids)
-        elif len(self.position_cache[layer_idx]) == 0:
-            self.position_cache[layer_idx] = position_ids
-        else:
-            self.position_cache[layer_idx] = torch.cat([self.position_cache[layer_idx], position_ids], dim=-1)
+            self._pos_buf.append(None)
+            self._pos_len.append(0)
+        n = position_ids.shape[-1]
+        buf, cur = self._pos_buf[layer_idx], self._pos_len[layer_idx]
+        if buf is None or cur + n > buf.shape[-1] or buf.shape[:-1] != position_ids.shape[:-1]:
+            cap = max(cur + n, int((0 if buf is None else buf.shape[-1]) * 1.5), 8192)
+            nb = torch.empty(position_ids.shape[:-1] + (cap,), dtype=position_ids.dtype, device=position_ids.device)
+            if cur:
+                nb[..., :cur].copy_(buf[..., :cur])
+            buf = self._pos_buf[layer_idx] = nb
+        buf[..., cur:cur + n].copy_(position_ids)
+        self._pos_len[layer_idx] = cur + n
+        self.position_cache[layer_idx] = buf[..., :cur + n]
         return self.position_cache[layer_idx]
 
     def get_prev_temporal_idx(self, layer_idx: int):
-        if len(self.position_cache) <= layer_idx:
+        if len(self.position_cache) <= layer_idx or len(self.position_cache[layer_idx]) == 0:
             return -1
         cache_layer = self.position_cache[layer_idx]
         return cache_layer[0, 0, -1] if cache_layer.ndim == 3 else cache_layer[0, -1]
 
-    def select_keep_indices(self, head_scores: torch.Tensor, keep_len: int) -> torch.Tensor:
-        """Hook between scoring and selection; the KV-head-sharded cache all-gathers ``head_scores`` here."""
-        return pivot_select(head_scores, keep_len, getattr(self, "keypatches_mask_chunk", None))
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        if layer_idx >= len(self.layers):
+            return 0
+        return self.layers[layer_idx].get_seq_length()
+
+    # ------------------------------------------------------------------------------------------------ update
+    def _compress_chunk(self, query_states, key_states, value_states, position_ids, rotary_emb_fn, mrope_section,
+                        keep_len):
+        """one ``rtk_pivot_update`` call -> (kept K [1,KVH,keep,D], kept V, kept positions or None)"""
+        q, H, L, D, qsh, qsl = _hld(query_states, "query_states")
+        k, KVH, Lk, Dk, ksh, ksl = _hld(key_states, "key_states")
+        v, _, _, _, vsh, vsl = _hld(value_states, "value_states")
+        if Lk != L or Dk != D:
+            raise ValueError("PivotKV scores the chunk's own keys: key and query lengths must match")
+        dev = q.device
+        lib = N.lib()
+        ws = _workspace(dev, int(lib.rtk_pivot_update_workspace_bytes(H, KVH, L, D)) + 256)
+        ws_ptr = (ws.data_ptr() + 255) & ~255
+        k_out = torch.empty((1, KVH, keep_len, D), dtype=torch.bfloat16, device=dev)
+        v_out = torch.empty_like(k_out)
+        head_scores = torch.empty((KVH, L), dtype=torch.bfloat16, device=dev)
+        keep_idx = torch.empty((keep_len,), dtype=torch.int32, device=dev)
+        a = _UpdateArgs()
+        a.q, a.H, a.q_stride_h, a.q_stride_l = q.data_ptr(), H, qsh, qsl
+        a.k, a.KVH, a.k_stride_h, a.k_stride_l = k.data_ptr(), KVH, ksh, ksl
+        a.v, a.v_stride_h, a.v_stride_l = v.data_ptr(), vsh, vsl
+        a.k_stride_h_in, a.k_stride_l_in = ksh, ksl
+        a.L, a.D, a.keep = L, D, keep_len
+        keymask = getattr(self, "keypatches_mask_chunk", None)
+        if keymask is not None:
+            N.require_cuda(keymask, "keypatches_mask_chunk", torch.bool)
+            keymask = keymask.contiguous()
+            if keymask.numel() != L:
+                raise ValueError("keypatches_mask_chunk must have one entry per chunk token")
+            a.keymask = keymask.data_ptr()
+        reforge = bool(self.pos_embed_reforge)
+        a.reforge = int(reforge)
+        pos_out = pos_flat = cos = sin = inv = None
+        if position_ids is not None:
+            N.require_cuda(position_ids, "position_ids", torch.int64)
+            pos_flat = position_ids.reshape(-1, L).contiguous()
+            a.n_pos, a.pos = pos_flat.shape[0], pos_flat.data_ptr()
+            pos_out = torch.empty(position_ids.shape[:-1] + (keep_len,), dtype=torch.int64, device=dev)
+            a.pos_out = pos_out.data_ptr()
+            if mrope_section and pos_flat.shape[0] == 3:
+                a.mrope_section = (C.c_int32 * 3)(*[int(s) for s in mrope_section])
+        fast = None
+        if reforge:
+            scaling = float(rotary_emb_fn.attention_scaling)
+            a.attention_scaling, a.inv_scale2 = scaling, _inv_scale2(scaling)
+            fast = _rotary_inv_freq(rotary_emb_fn)
+            if fast is not None:
+                inv = fast[0].to(device=dev, dtype=torch.float32).contiguous()
+                a.inv_freq = inv.data_ptr()
+            else:
+                cos, sin = rotary_emb_fn(value_states, position_ids)
+                cos, sin = cos.contiguous(), sin.contiguous()
+                if cos.dtype != torch.bfloat16 or cos.numel() != pos_flat.shape[0] * L * D:
+                    raise ValueError("rotary_emb must return bf16 [n_pos, 1, L, D] tables")
+                a.cos, a.sin = cos.data_ptr(), sin.data_ptr()
+        a.k_out, a.v_out, a.out_stride_h = k_out.data_ptr(), v_out.data_ptr(), keep_len * D
+        a.keep_idx, a.head_scores = keep_idx.data_ptr(), head_scores.data_ptr()
+        a.workspace, a.workspace_bytes = ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr())
+        if self.score_events is not None:
+            a.ev_score_begin, a.ev_score_end = self.score_events
+            self.score_events = None
+        with torch.cuda.device(dev):
+            N.check(lib.rtk_pivot_update(C.byref(a), N.stream_ptr(dev)), "rtk_pivot_update")
+        if reforge and fast is None:
+            # opaque rotary callable: ask it for the tables of the re-indexed positions, then re-rotate in place
+            cos2, sin2 = rotary_emb_fn(v_out, pos_out)
+            pivot_rope(k_out, cos2, sin2, mrope_section, 1.0, forward=True, out=k_out)
+        self.last_head_scores, self.last_keep_indices = head_scores, keep_idx
+        return k_out, v_out, pos_out
 
     def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int,
                cache_kwargs: Optional[Dict[str, Any]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -254,8 +507,13 @@ class PivotKVCache(DynamicCache):
         cache_kwargs = cache_kwargs if cache_kwargs is not None else {}
         position_ids = cache_kwargs.pop("position_ids", None)
 
+        # the previous layer's attention is on the stream by now: its kept rows may land
+        self.flush()
         # 1) this chunk attends to everything: [past | chunk] is what the caller gets back
-        key_states_output, value_states_output = super().update(key_states, value_states, layer_idx)
+        while len(self.layers) <= layer_idx:
+            self.layers.append(PivotKVLayer())
+        layer = self.layers[layer_idx]
+        key_states_output, value_states_output = layer.update(key_states, value_states)
 
         if self.kvcache_compression:
             query_states = cache_kwargs.pop("query_states")
@@ -264,34 +522,20 @@ class PivotKVCache(DynamicCache):
             bsz, num_heads, q_len, head_dim = query_states.shape
             num_key_value_heads, k_len = key_states.shape[1:3]
             assert bsz == 1
-            if self.pos_embed_reforge and position_ids is None:
-                raise ValueError("pos_embed_reforge needs position_ids in cache_kwargs")
-
-            if self.pos_embed_reforge:
-                cos, sin = rotary_emb_fn(value_states, position_ids)
-                scaling = rotary_emb_fn.attention_scaling
-                query_states = pivot_rope(query_states, cos, sin, mrope_section, scaling, forward=False)
-                key_states = pivot_rope(key_states, cos, sin, mrope_section, scaling, forward=False)
+            if self.pos_embed_reforge and (position_ids is None or rotary_emb_fn is None):
+                raise ValueError("pos_embed_reforge needs position_ids and rotary_emb in cache_kwargs")
 
             # 2) score the chunk's own keys with the chunk's queries, keep the top ratio * q_len
             keep_len = max(1, int(self.compression_ratio * q_len))
-            head_scores = pivot_head_scores(query_states, key_states)
-            keep_indices = self.select_keep_indices(head_scores, keep_len)
-            self.last_head_scores, self.last_keep_indices = head_scores, keep_indices
-
-            compressed_key_states, compressed_value_states, compressed_position_ids = pivot_compact(
-                key_states, value_states, keep_indices, position_ids, reforge=self.pos_embed_reforge)
-
+            kept_k, kept_v, kept_pos = self._compress_chunk(query_states, key_states, value_states, position_ids,
+                                                            rotary_emb_fn, mrope_section, keep_len)
             if self.pos_embed_reforge:
-                cos, sin = rotary_emb_fn(compressed_value_states, compressed_position_ids)
-                pivot_rope(compressed_key_states, cos, sin, mrope_section, 1.0, forward=True, out=compressed_key_states)
-                self.update_position_ids(compressed_position_ids, layer_idx)
+                self.update_position_ids(kept_pos, layer_idx)
             self.update_num_evicted_tokens(k_len - keep_len, layer_idx)
 
             # 3) cache keeps [past | kept]
-            layer = self.layers[layer_idx]
-            layer.keys = torch.cat([key_states_output[..., :-q_len, :], compressed_key_states], dim=2)
-            layer.values = torch.cat([value_states_output[..., :-q_len, :], compressed_value_states], dim=2)
+            layer.replace_tail(q_len, kept_k, kept_v)
+            self._dirty.append(layer)
         else:
             if self.pos_embed_reforge:
                 self.update_position_ids(position_ids, layer_idx)
