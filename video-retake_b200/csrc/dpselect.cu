@@ -81,25 +81,25 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
     }
 
     const float eps = __uint_as_float(0x322c0000u);          // bf16(1e-8) widened (clamp_min_ on a bf16 tensor)
-    uint2 up[K4];                                            // previous row, normalised, bf16x2 packed
     int consumed = 0;
-    while (cons.valid()) {
+    // one row: wait for its bytes, reduce the norm, refill the ring slot, normalise into `cur`, and (unless it is the
+    // first row of an item) emit the distance against `prev`.  Called with the two register files swapped on
+    // alternate rows so that "previous row" never has to be copied.
+    auto process_row = [&](uint2 (&cur)[K4], const uint2 (&prev)[K4]) {
         const int s = consumed % stages;
         mbar_wait(bars + 8u * s, (uint32_t)(consumed / stages) & 1u);
         const uint8_t* row = ring + (size_t)s * row_bytes;
-        uint2 xr[K4];
 #pragma unroll
         for (int k = 0; k < K4; ++k) {
             const int v = lane + 32 * k;
-            xr[k] = (v < nv4) ? *reinterpret_cast<const uint2*>(row + 8 * v) : make_uint2(0u, 0u);
+            cur[k] = (v < nv4) ? *reinterpret_cast<const uint2*>(row + 8 * v) : make_uint2(0u, 0u);
         }
         // ---- norm: 4 accumulators per lane, sequential over k (ATen Reduce.cuh, input_vec_size 4)
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
         for (int k = 0; k < K4; ++k) {
-            const float e0 = bf16lo_to_f32(xr[k].x), e1 = bf16hi_to_f32(xr[k].x);
-            const float e2 = bf16lo_to_f32(xr[k].y), e3 = bf16hi_to_f32(xr[k].y);
-            a0 = fmaf(e0, e0, a0); a1 = fmaf(e1, e1, a1); a2 = fmaf(e2, e2, a2); a3 = fmaf(e3, e3, a3);
+            fma_sq_bf16x2(a0, a1, cur[k].x);
+            fma_sq_bf16x2(a2, a3, cur[k].y);
         }
         float ss = ((a0 + a1) + a2) + a3;
 #pragma unroll
@@ -114,8 +114,8 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
         const float rcp = __frcp_rn(nrm);
 #pragma unroll
         for (int k = 0; k < K4; ++k) {
-            xr[k].x = pack_bf16x2_rn(bf16lo_to_f32(xr[k].x) * rcp, bf16hi_to_f32(xr[k].x) * rcp);
-            xr[k].y = pack_bf16x2_rn(bf16lo_to_f32(xr[k].y) * rcp, bf16hi_to_f32(xr[k].y) * rcp);
+            cur[k].x = scale_bf16x2_rn(cur[k].x, rcp);
+            cur[k].y = scale_bf16x2_rn(cur[k].y, rcp);
         }
         if (cons.f != cons.fbeg) {
             // ---- sum of rounded products in the 8-element-vector order (Reduce.cuh, input_vec_size 8):
@@ -124,14 +124,14 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
             float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
 #pragma unroll
             for (int k = 0; k < K4; ++k) {
-                const uint32_t p01 = mul_bf16x2_rn(up[k].x, xr[k].x);
-                const uint32_t p23 = mul_bf16x2_rn(up[k].y, xr[k].y);
+                const uint32_t p01 = mul_bf16x2_rn(prev[k].x, cur[k].x);
+                const uint32_t p23 = mul_bf16x2_rn(prev[k].y, cur[k].y);
                 if ((k & 1) == 0) {
-                    e0 += bf16lo_to_f32(p01); e1 += bf16hi_to_f32(p01);
-                    e2 += bf16lo_to_f32(p23); e3 += bf16hi_to_f32(p23);
+                    add_bf16x2(e0, e1, p01);
+                    add_bf16x2(e2, e3, p23);
                 } else {
-                    o0 += bf16lo_to_f32(p01); o1 += bf16hi_to_f32(p01);
-                    o2 += bf16lo_to_f32(p23); o3 += bf16hi_to_f32(p23);
+                    add_bf16x2(o0, o1, p01);
+                    add_bf16x2(o2, o3, p23);
                 }
             }
             const float se = ((e0 + e1) + e2) + e3;          // accumulators 0..3 of 8-lane l' (even lanes)
@@ -149,10 +149,14 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
         } else if (cons.f == 0 && !halo) {
             if (lane == 0) dis[cons.p] = 1.0f;
         }
-#pragma unroll
-        for (int k = 0; k < K4; ++k) up[k] = xr[k];
         ++consumed;
         cons.advance();
+    };
+    uint2 ra[K4], rb[K4];                                    // normalised rows, bf16x2 packed (ping-pong)
+    while (cons.valid()) {
+        process_row(ra, rb);
+        if (!cons.valid()) break;
+        process_row(rb, ra);
     }
 }
 
@@ -243,9 +247,22 @@ dpselect_select_patch_kernel(const float* __restrict__ dis, int T, int N, int t,
     uint8_t* spk = smem + (size_t)kSelWarps * T * 4;          // [8][T] peak flags
     const int p0 = blockIdx.x * kSelWarps;
     const int np = min(kSelWarps, N - p0);
-    for (int i = threadIdx.x; i < T * kSelWarps; i += blockDim.x) {
-        const int tt = i / kSelWarps, j = i - tt * kSelWarps;
-        if (j < np) sd[j * T + tt] = dis[(size_t)tt * N + p0 + j];
+    {   // thread (tt0, j) walks frames tt0, tt0+32, ...; 8 independent loads in flight per thread
+        const int j = threadIdx.x & (kSelWarps - 1), tt0 = threadIdx.x / kSelWarps;
+        constexpr int kStep = kSelWarps * kWarp / kSelWarps;          // frames covered per sweep of the block
+        if (j < np) {
+            const float* src = dis + p0 + j;
+            float* dst = sd + j * T;
+            int tt = tt0;
+            for (; tt + 7 * kStep < T; tt += 8 * kStep) {
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldg(src + (size_t)(tt + u * kStep) * N);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) dst[tt + u * kStep] = v[u];
+            }
+            for (; tt < T; tt += kStep) dst[tt] = __ldg(src + (size_t)tt * N);
+        }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

@@ -318,8 +318,8 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
         while (range.next(u, tb0, tb1)) {
             const int h = u / nt, ta = u - h * nt;
             float m = -INFINITY;                 // pass 1: running max (scaled-logit domain)
-            uint64_t acc = pk2(0.f, 0.f);        // pass 1: row sum (two interleaved halves)
-            float c0 = 0.f, c1 = 0.f;            // pass 2: column sum (two interleaved halves)
+            uint64_t acc = pk2(0.f, 0.f), acc_b = pk2(0.f, 0.f);   // pass 1: row sum (independent chains)
+            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;          // pass 2: column sum (independent chains)
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 if ((int)(cnt & 1u) != (grp >> 1)) continue;
                 const int b = cnt % kAccBufs;
@@ -345,24 +345,28 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                                 if (j * 16 + i >= valid) r[i] = 0xff800000u;     // -inf: padded key column
                         }
                         // the rounding chain is monotone, so the row max of the rounded logits is the chain of the raw max
-                        float mx = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
+                        float m4[4];
 #pragma unroll
-                        for (int i = 3; i < 15; i += 2)
-                            mx = fmaxf(fmaxf(mx, __uint_as_float(r[i])), __uint_as_float(r[i + 1]));
-                        mx = fmaxf(mx, __uint_as_float(r[15]));
+                        for (int i = 0; i < 4; ++i)             // four independent 3-input maxima, then a short fold
+                            m4[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                                          fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+                        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
                         const float mn = fmaxf(m, logit_chain1(mx, inv));
                         if (__any_sync(0xffffffffu, mn > m)) {                     // rare after the first few steps
                             const float sc = (mn > -INFINITY) ? ex2f((m - mn) * kLog2e) : 0.f;   // m == -inf -> 0
                             acc = mul2(acc, pk2(sc, sc));
+                            acc_b = mul2(acc_b, pk2(sc, sc));
                             m = mn;
                         }
                         const float mm = (m > -INFINITY) ? m * kLog2e : 0.f;
                         const uint64_t nmm = pk2(-mm, -mm);
 #pragma unroll
-                        for (int i = 0; i < 16; i += 2) {
-                            float y0, y1;
+                        for (int i = 0; i < 16; i += 4) {
+                            float y0, y1, y2, y3;
                             upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), y0, y1);
+                            upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, nmm), y2, y3);
                             acc = add2(acc, pk2(ex2f(y0), ex2f(y1)));
+                            acc_b = add2(acc_b, pk2(ex2f(y2), ex2f(y3)));
                         }
                     } else {
 #pragma unroll
@@ -372,7 +376,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                             upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y)), y0, y1);
                             upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w)), y2, y3);
                             add_bf16_pair(c0, c1, pack_bf16x2_rn(ex2f(y0), ex2f(y1)));
-                            add_bf16_pair(c0, c1, pack_bf16x2_rn(ex2f(y2), ex2f(y3)));
+                            add_bf16_pair(c2, c3, pack_bf16x2_rn(ex2f(y2), ex2f(y3)));
                         }
                     }
                     if (j < 3) tmem_ld_wait16(rn);
@@ -383,8 +387,8 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
             }
             // ---- fold the four groups and write this CTA's share of the unit
             float a0, a1;
-            upk2(acc, a0, a1);
-            if (PASS == 2) { a0 = c0; a1 = c1; }
+            upk2(add2(acc, acc_b), a0, a1);
+            if (PASS == 2) { a0 = c0 + c2; a1 = c1 + c3; }
             const int part = (tb0 == 0) ? 0 : 1;
             const bool whole = (tb0 == 0) && (tb1 == nt);
             const size_t o = (size_t)h * nt * kTile + (size_t)ta * kTile + row;

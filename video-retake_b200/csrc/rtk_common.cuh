@@ -43,6 +43,30 @@ __device__ __forceinline__ uint32_t mul_bf16x2_rn(uint32_t a, uint32_t b) {
     return d;
 }
 
+// Mixed-precision fp32 accumulate straight from the halves of a packed bf16x2 register (sm_100: SASS FHFMA.BF16 /
+// FHADD.BF16) - no widening instructions.  acc_lo += lo(p)*lo(p), acc_hi += hi(p)*hi(p)
+__device__ __forceinline__ void fma_sq_bf16x2(float& acc_lo, float& acc_hi, uint32_t p) {
+    asm("{\n\t.reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %2;\n\t"
+        "fma.rn.f32.bf16 %0, lo, lo, %0;\n\t"
+        "fma.rn.f32.bf16 %1, hi, hi, %1;\n\t}"
+        : "+f"(acc_lo), "+f"(acc_hi)
+        : "r"(p));
+}
+// acc_lo += lo(p), acc_hi += hi(p)
+__device__ __forceinline__ void add_bf16x2(float& acc_lo, float& acc_hi, uint32_t p) {
+    asm("{\n\t.reg .b16 lo, hi;\n\t"
+        "mov.b32 {lo, hi}, %2;\n\t"
+        "add.rn.f32.bf16 %0, lo, %0;\n\t"
+        "add.rn.f32.bf16 %1, hi, %1;\n\t}"
+        : "+f"(acc_lo), "+f"(acc_hi)
+        : "r"(p));
+}
+// (lo, hi) of a packed bf16x2 times a scalar, rounded back to bf16x2
+__device__ __forceinline__ uint32_t scale_bf16x2_rn(uint32_t p, float s) {
+    return pack_bf16x2_rn(bf16lo_to_f32(p) * s, bf16hi_to_f32(p) * s);
+}
+
 // Radix order used by ATen's CUDA top-k (SortingRadixSelect.cuh TopKTypeConfig<float>): NaN is the largest
 // key, -0 sorts below +0.
 __device__ __forceinline__ uint32_t f32_to_ordered(float v) {
