@@ -17,6 +17,13 @@
 
 #include "rtk_common.cuh"
 
+#ifndef RTK_SCORE_EXPERIMENT_NOMATH
+#define RTK_SCORE_EXPERIMENT_NOMATH 0
+#endif
+#ifndef RTK_SCORE_EXPERIMENT_NOEXP
+#define RTK_SCORE_EXPERIMENT_NOEXP 0
+#endif
+
 namespace rtk {
 
 constexpr int kTile = 128;            // rows of both operand tiles, = UMMA M = UMMA N
@@ -108,9 +115,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 __device__ __forceinline__ float ex2f(float x) {
+#if RTK_SCORE_EXPERIMENT_NOEXP             // timing experiment: everything but the MUFU
+    return x * 0.5f;
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 __device__ __forceinline__ float lg2f(float x) {
     float y;
@@ -173,6 +184,122 @@ __device__ __forceinline__ uint64_t logit_chain2(uint32_t r0, uint32_t r1, uint6
     return widen2(pack_bf16x2_rn(s0, s1));
 }
 __device__ __forceinline__ float logit_chain1(float acc, float inv) { return round_bf16(round_bf16(acc) * inv); }
+
+#ifndef RTK_SCORE_X16
+#define RTK_SCORE_X16 0        // 16-column TMEM loads, double buffered (1) vs 32-column blocking loads (0)
+#endif
+#ifndef RTK_SCORE_FHADD
+#define RTK_SCORE_FHADD 0      // pass 2: accumulate bf16 halves with FHADD.BF16 (1) vs widen + packed fp32 add (0)
+#endif
+#ifndef RTK_SCORE_LAZY
+#define RTK_SCORE_LAZY 0       // pass 1: rescale only when some lane's maximum grew (1) vs every step (0)
+#endif
+#ifndef RTK_SCORE_TREEMAX
+#define RTK_SCORE_TREEMAX 0
+#endif
+#ifndef RTK_SCORE_EXPERIMENT_EX2_BF16X2
+#define RTK_SCORE_EXPERIMENT_EX2_BF16X2 0
+#endif
+#ifndef RTK_SCORE_CHAINS
+#define RTK_SCORE_CHAINS 1     // independent accumulation chains
+#endif
+
+struct SoftmaxState {
+    float m = -INFINITY;                                     // pass 1: running max (scaled-logit domain)
+    uint64_t acc = 0, acc_b = 0;                             // packed fp32x2 sums (pass 1 row sum / pass 2 column sum)
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;            // pass 2 column sums when FHADD is used
+};
+
+// NC consecutive accumulator columns of one TMEM lane (one row of the stationary tile)
+template <int PASS, int NC>
+__device__ __forceinline__ void softmax_cols(uint32_t (&r)[NC], int col0, int valid, SoftmaxState& st, const float* cq,
+                                             float inv, uint64_t inv2, uint64_t l2e2) {
+#if RTK_SCORE_EXPERIMENT_NOMATH            // timing experiment: MMA + TMEM load pipeline only
+    {
+        float mx = __uint_as_float(r[0]);
+#pragma unroll
+        for (int i = 1; i < NC; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        st.m = fmaxf(st.m, mx);
+        return;
+    }
+#endif
+    if (PASS == 1) {
+        if (valid < 64) {
+#pragma unroll
+            for (int i = 0; i < NC; ++i)
+                if (col0 + i >= valid) r[i] = 0xff800000u;   // -inf: padded key column
+        }
+        // the rounding chain is monotone, so the row max of the rounded logits is the chain of the raw max
+#if RTK_SCORE_TREEMAX
+        float m4[NC / 4];
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i)
+            m4[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                          fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+        float mx = m4[0];
+#pragma unroll
+        for (int i = 1; i < NC / 4; ++i) mx = fmaxf(mx, m4[i]);
+#else
+        float mx = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
+#pragma unroll
+        for (int i = 3; i < NC - 1; i += 2) mx = fmaxf(fmaxf(mx, __uint_as_float(r[i])), __uint_as_float(r[i + 1]));
+        mx = fmaxf(mx, __uint_as_float(r[NC - 1]));
+#endif
+        const float mn = fmaxf(st.m, logit_chain1(mx, inv));
+#if RTK_SCORE_LAZY
+        if (__any_sync(0xffffffffu, mn > st.m)) {            // rare after the first few steps
+            const float sc = (mn > -INFINITY) ? ex2f((st.m - mn) * kLog2e) : 0.f;
+            st.acc = mul2(st.acc, pk2(sc, sc));
+            st.acc_b = mul2(st.acc_b, pk2(sc, sc));
+            st.m = mn;
+        }
+        const float mm = (st.m > -INFINITY) ? st.m * kLog2e : 0.f;
+#else
+        if (!(mn > -INFINITY)) return;
+        const float mm = mn * kLog2e;
+        const float sc = ex2f(fmaf(st.m, kLog2e, -mm));      // m == -inf -> 0
+        st.acc = mul2(st.acc, pk2(sc, sc));
+        if (RTK_SCORE_CHAINS > 1) st.acc_b = mul2(st.acc_b, pk2(sc, sc));
+        st.m = mn;
+#endif
+        const uint64_t nmm = pk2(-mm, -mm);
+#pragma unroll
+        for (int i = 0; i < NC; i += 4) {
+            float y0, y1, y2, y3;
+            upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), y0, y1);
+            upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, nmm), y2, y3);
+#if RTK_SCORE_EXPERIMENT_EX2_BF16X2       // throughput experiment only (8-bit exps are not accurate enough)
+            uint32_t e01 = pack_bf16x2_rn(y0, y1), e23 = pack_bf16x2_rn(y2, y3);
+            asm("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(e01));
+            asm("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(e23));
+            st.acc = add2(st.acc, widen2(e01));
+            st.acc = add2(st.acc, widen2(e23));
+#else
+            st.acc = add2(st.acc, pk2(ex2f(y0), ex2f(y1)));
+            if (RTK_SCORE_CHAINS > 1) st.acc_b = add2(st.acc_b, pk2(ex2f(y2), ex2f(y3)));
+            else st.acc = add2(st.acc, pk2(ex2f(y2), ex2f(y3)));
+#endif
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < NC; i += 4) {
+            const float4 cc = *reinterpret_cast<const float4*>(cq + col0 + i);
+            float y0, y1, y2, y3;
+            upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y)), y0, y1);
+            upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w)), y2, y3);
+            const uint32_t p01 = pack_bf16x2_rn(ex2f(y0), ex2f(y1)), p23 = pack_bf16x2_rn(ex2f(y2), ex2f(y3));
+#if RTK_SCORE_FHADD
+            add_bf16_pair(st.c0, st.c1, p01);
+            if (RTK_SCORE_CHAINS > 1) add_bf16_pair(st.c2, st.c3, p23);
+            else add_bf16_pair(st.c0, st.c1, p23);
+#else
+            st.acc = add2(st.acc, widen2(p01));
+            if (RTK_SCORE_CHAINS > 1) st.acc_b = add2(st.acc_b, widen2(p23));
+            else st.acc = add2(st.acc, widen2(p23));
+#endif
+        }
+    }
+}
 
 // One CTA's share of the flattened (unit, streamed tile) space: a contiguous range, so every SM gets the same
 // number of tile-steps (+-1) and a unit is shared by at most two CTAs (range length >= nt).
@@ -317,9 +444,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
         uint32_t cnt = 0;
         while (range.next(u, tb0, tb1)) {
             const int h = u / nt, ta = u - h * nt;
-            float m = -INFINITY;                 // pass 1: running max (scaled-logit domain)
-            uint64_t acc = pk2(0.f, 0.f), acc_b = pk2(0.f, 0.f);   // pass 1: row sum (independent chains)
-            float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;          // pass 2: column sum (independent chains)
+            SoftmaxState st;
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 if ((int)(cnt & 1u) != (grp >> 1)) continue;
                 const int b = cnt % kAccBufs;
@@ -329,6 +454,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 const int valid = prm.L - tb * kTile - half * 64;      // streamed rows of this half that exist
                 const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + half * 64;
                 const uint32_t taddr = lane_addr + b * kTile;
+#if RTK_SCORE_X16
                 // 64 columns in four 16-column steps; the TMEM load of step j+1 is in flight while step j is computed
                 uint32_t ra[16], rb[16];
                 tmem_ld16(taddr, ra);
@@ -338,57 +464,27 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                     uint32_t (&r)[16] = (j & 1) ? rb : ra;
                     uint32_t (&rn)[16] = (j & 1) ? ra : rb;
                     if (j < 3) tmem_ld16(taddr + (j + 1) * 16, rn);
-                    if (PASS == 1) {
-                        if (valid < 64) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                if (j * 16 + i >= valid) r[i] = 0xff800000u;     // -inf: padded key column
-                        }
-                        // the rounding chain is monotone, so the row max of the rounded logits is the chain of the raw max
-                        float m4[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)             // four independent 3-input maxima, then a short fold
-                            m4[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
-                                          fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
-                        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-                        const float mn = fmaxf(m, logit_chain1(mx, inv));
-                        if (__any_sync(0xffffffffu, mn > m)) {                     // rare after the first few steps
-                            const float sc = (mn > -INFINITY) ? ex2f((m - mn) * kLog2e) : 0.f;   // m == -inf -> 0
-                            acc = mul2(acc, pk2(sc, sc));
-                            acc_b = mul2(acc_b, pk2(sc, sc));
-                            m = mn;
-                        }
-                        const float mm = (m > -INFINITY) ? m * kLog2e : 0.f;
-                        const uint64_t nmm = pk2(-mm, -mm);
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            float y0, y1, y2, y3;
-                            upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), y0, y1);
-                            upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, nmm), y2, y3);
-                            acc = add2(acc, pk2(ex2f(y0), ex2f(y1)));
-                            acc_b = add2(acc_b, pk2(ex2f(y2), ex2f(y3)));
-                        }
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 16; i += 4) {
-                            const float4 cc = *reinterpret_cast<const float4*>(cq + j * 16 + i);
-                            float y0, y1, y2, y3;
-                            upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y)), y0, y1);
-                            upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w)), y2, y3);
-                            add_bf16_pair(c0, c1, pack_bf16x2_rn(ex2f(y0), ex2f(y1)));
-                            add_bf16_pair(c2, c3, pack_bf16x2_rn(ex2f(y2), ex2f(y3)));
-                        }
-                    }
+                    softmax_cols<PASS, 16>(r, j * 16, valid, st, cq, inv, inv2, l2e2);
                     if (j < 3) tmem_ld_wait16(rn);
                 }
+#else
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 32>(r, c * 32, valid, st, cq, inv, inv2, l2e2);
+                }
+#endif
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty(b));
             }
+            const float m = st.m;
             // ---- fold the four groups and write this CTA's share of the unit
             float a0, a1;
-            upk2(add2(acc, acc_b), a0, a1);
-            if (PASS == 2) { a0 = c0 + c2; a1 = c1 + c3; }
+            upk2(add2(st.acc, st.acc_b), a0, a1);
+            if (PASS == 2 && RTK_SCORE_FHADD) { a0 = st.c0 + st.c2; a1 = st.c1 + st.c3; }
             const int part = (tb0 == 0) ? 0 : 1;
             const bool whole = (tb0 == 0) && (tb1 == nt);
             const size_t o = (size_t)h * nt * kTile + (size_t)ta * kTile + row;
