@@ -70,6 +70,11 @@ int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64_t t, int s
 int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t C, const int32_t* idx, int64_t t,
                         int sync, void* out, void* stream);
 
+/* Generic row gather out[i, :] = x[src_row[i], :] (rows of row_bytes, a multiple of 16).  Used when DPSelect is split
+ * by frame range across GPUs: every rank compacts only the survivors it owns (visual_compression.py:173 restricted
+ * to a frame range).  src_row is int64 [rows] on the device. */
+int rtk_gather_rows(const void* x, int64_t row_bytes, const int64_t* src_row, int64_t rows, void* out, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * PivotKV  (retake/longvideo_cache.py)
  * ---------------------------------------------------------------------------------------------------- */

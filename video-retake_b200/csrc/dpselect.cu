@@ -391,6 +391,28 @@ dpselect_gather_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ 
     }
 }
 
+// generic row gather: out[i, :] = x[src_row[i], :], rows of nvec 16-byte vectors (frame-range-sharded compaction)
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ x, const long long* __restrict__ src_row, uint4* __restrict__ out, int nvec,
+                   long long rows) {
+    const int lane = threadIdx.x & 31;
+    const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long GW = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = gw; r < rows; r += GW) {
+        const uint4* src = x + (size_t)src_row[r] * nvec;
+        uint4* dst = out + (size_t)r * nvec;
+        int v = lane;
+        for (; v + 7 * 32 < nvec; v += 8 * 32) {
+            uint4 b[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) b[u] = __ldg(src + v + 32 * u);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) dst[v + 32 * u] = b[u];
+        }
+        for (; v < nvec; v += 32) dst[v] = __ldg(src + v);
+    }
+}
+
 }  // namespace rtk
 
 // =================================================================================================== C ABI
@@ -456,6 +478,23 @@ extern "C" int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t 
     if (grid > (long long)sms * 8) grid = (long long)sms * 8;
     dpselect_gather_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)x, idx, (uint4*)out, (int)N, (int)(C / 8), rows, sync);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rtk_gather_rows(const void* x, int64_t row_bytes, const int64_t* src_row, int64_t rows, void* out,
+                               void* stream) {
+    if (!x || !src_row || !out || rows < 0 || row_bytes < 16) return RTK_E_BADARG;
+    if (row_bytes % 16 != 0) return RTK_E_UNSUPPORTED;
+    if ((((uintptr_t)x | (uintptr_t)out) & 15u) != 0) return RTK_E_ALIGN;
+    if (rows == 0) return 0;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long grid = (rows + 7) / 8;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    gather_rows_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const uint4*)x, (const long long*)src_row,
+                                                                        (uint4*)out, (int)(row_bytes / 16), rows);
     RTK_CHECK_LAUNCH();
     return 0;
 }

@@ -38,6 +38,7 @@ def lib() -> C.CDLL:
         "rtk_dpselect_dis": ([p, i64, i64, i64, i32, p, p], C.c_int),
         "rtk_dpselect_select": ([p, i64, i64, i64, i32, p, p, p], C.c_int),
         "rtk_dpselect_gather": ([p, i64, i64, i64, p, i64, i32, p, p], C.c_int),
+        "rtk_gather_rows": ([p, i64, p, i64, p, p], C.c_int),
         "rtk_pivot_rope": ([p, i64, i64, i64, i64, i64, p, p, i32, p, f32, i32, p, i64, i64, p], C.c_int),
         "rtk_pivot_score_workspace_bytes": ([i64, i64], sz),
         "rtk_pivot_score": ([p, i64, i64, i64, p, i64, i64, i64, i64, i64, p, p, sz, p], C.c_int),
@@ -57,7 +58,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTS = ("rtk_version", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
-           "rtk_dpselect_gather", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
+           "rtk_dpselect_gather", "rtk_gather_rows", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
            "rtk_pivot_select", "rtk_pivot_compact", "rtk_pivot_rope_tables", "rtk_pivot_update_workspace_bytes",
            "rtk_pivot_update")
 
