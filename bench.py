@@ -28,6 +28,8 @@ for p in (ROOT, os.path.join(ROOT, "video-retake_b200"), os.path.join(ROOT, "tes
     if p not in sys.path:
         sys.path.insert(0, p)
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the one JSON line
+
 import torch  # noqa: E402
 
 METRIC = "2048-frame DPSelect+PivotKV frames/s"
@@ -118,6 +120,7 @@ class ScoreTimer:
 
     def __init__(self, every=8):
         self.every, self.n, self.pairs, self.on = every, 0, [], False
+        self.dpselect = []
 
     def arm(self, cache):
         self.n += 1
@@ -135,7 +138,13 @@ class ScoreTimer:
 
 def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer=None):
     """one video through the public operators; returns a small device tensor standing for the step's result"""
+    if timer is not None and timer.on:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
     out, mask = vc.memory_bank_compress_keyframe(x[None], s.t, 3, sync=False)
+    if timer is not None and timer.on:
+        b.record()
+        timer.dpselect.append((a, b))
     cache = lc.build_kvcache(cache_config(s))
     pool = q.shape[0]
     it = 0
@@ -346,12 +355,23 @@ def main():
     roofline = {"kernel": "pivot_score_kernel<1> + pivot_score_kernel<2> (one rtk_pivot_score call)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "achieved_executed": 2 * achieved, "frac_executed": 2 * achieved / peak_tf, "peak_source": peak_src,
-                "ms_per_call": score_ms, "calls_timed": len(timer.pairs), "traffic": None,
-                "note": "algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it twice"}
+                "ms_per_call": score_ms, "calls_timed": len(timer.pairs),
+                # dram__bytes_read.sum + dram__bytes_write.sum of both launches, profiles/r1_ncu_score_summary.txt (L=4096)
+                "traffic": 67.6e6 if s.L == 4096 else None,
+                "note": ("algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it twice and is bounded by the "
+                         "TMEM read port, not the tensor pipe (DESIGN.md section 5)")}
+    dps_ms = sum(a.elapsed_time(b) for a, b in timer.dpselect) / max(1, len(timer.dpselect))
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    dps_bytes = 2.0 * s.T * s.N * s.C + 4.0 * s.T * s.N + 4.0 * s.t * s.N * s.C
+    dpselect_roofline = {"kernels": "dpselect_dis + dpselect_select_patch + dpselect_gather (one operator call)", "bound": "hbm",
+                         "achieved": dps_bytes / (dps_ms * 1e-3) / 1e9 if dps_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
+                         "frac": (dps_bytes / (dps_ms * 1e-3) / 1e9 / hbm) if dps_ms > 0 else 0.0, "ms_per_call": dps_ms,
+                         "algorithmic_bytes": dps_bytes}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic", "config": config, "roofline": roofline, "gpu_launches": int(launches)}
+            "data": "synthetic", "config": config, "roofline": roofline, "roofline_dpselect": dpselect_roofline,
+            "gpu_launches": int(launches)}
     if e2e is not None:
         line["e2e"] = e2e
     if clocks is not None:

@@ -47,8 +47,9 @@ struct RowCursor {
     }
 };
 
+// short rows (K4 <= 16, <= 120 registers) run two CTAs per SM so that 16 warps hide the per-row reduction latency
 template <int K4>
-__global__ void __launch_bounds__(kDisThreads, 1)
+__global__ void __launch_bounds__(kDisThreads, (K4 <= 16) ? 2 : 1)
 dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis, int T, int N, int C, int R,
                     int n_items, int stages, int halo) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -172,13 +173,14 @@ static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t row_bytes = (size_t)C * 2;
-    int stages = (int)(((size_t)smem_max - 1024) / (kDisWarps * row_bytes));
+    const int ctas_per_sm = (K4 <= 16) ? 2 : 1;
+    int stages = (int)(((size_t)smem_max / ctas_per_sm - 2048) / (kDisWarps * row_bytes));
     if (stages > 8) stages = 8;
     if (stages < 2) return RTK_E_UNSUPPORTED;
     const size_t smem = (size_t)kDisWarps * stages * row_bytes + (size_t)kDisWarps * stages * 8;
     // run length: long enough that the halo re-read is small, short enough to give every warp >= 4 items
     const long long frames = T - 1;
-    const long long warps = (long long)sms * kDisWarps;
+    const long long warps = (long long)sms * kDisWarps * ctas_per_sm;
     long long R = (frames * N) / (warps * 4);
     if (R > 32) R = 32;
     if (R < 4) R = 4;
@@ -186,7 +188,7 @@ static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, 
     const long long runs = (frames + R - 1) / R;
     const long long n_items = runs * N;
     long long grid = (n_items + kDisWarps - 1) / kDisWarps;
-    if (grid > sms) grid = sms;
+    if (grid > (long long)sms * ctas_per_sm) grid = (long long)sms * ctas_per_sm;
     auto kern = dpselect_dis_kernel<K4>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
