@@ -1,0 +1,66 @@
+"""CPU: host logic of the monkeypatch layer (no kernels): config patching, segmentation, chunk sizes, M-RoPE ids,
+sequence truncation bookkeeping of compress_video_tokens with visual compression off."""
+import types
+
+import pytest
+import torch
+
+from retake import monkeypatch
+
+
+def test_patch_config_functions_attach_longvideo_kwargs_and_yarn():
+    exp = {"method": "retake", "scaling_factor": 4, "longvideo_kwargs": {"chunked_prefill_frames": 32}}
+    cfg = types.SimpleNamespace(rope_scaling={"type": "mrope", "mrope_section": [16, 24, 24]})
+    out = monkeypatch.patch_qwen2vl_config(cfg, exp)
+    assert out is cfg and cfg.longvideo_kwargs == {"chunked_prefill_frames": 32}
+    assert cfg.rope_scaling == {"mrope_section": [16, 24, 24], "rope_type": "yarn", "factor": 4, "beta_fast": 32.0, "beta_slow": 1.0}
+    cfg2 = types.SimpleNamespace(text_config=types.SimpleNamespace(rope_parameters={"rope_type": "default", "rope_theta": 1e6}))
+    monkeypatch.patch_llava_onevision_config(cfg2, exp)
+    assert cfg2.text_config.rope_parameters == {"rope_type": "yarn", "factor": 4, "beta_fast": 32.0, "beta_slow": 1.0, "rope_theta": 1e6}
+    cfg3 = types.SimpleNamespace(rope_scaling={"type": "mrope"})
+    monkeypatch.patch_qwen2vl_config(cfg3, {})
+    assert cfg3.longvideo_kwargs == {} and cfg3.rope_scaling == {"type": "mrope"}
+
+
+def test_unknown_method_raises_like_the_reference():
+    with pytest.raises(NotImplementedError):
+        monkeypatch.patch_qwen2vl("h2o")
+    with pytest.raises(NotImplementedError):
+        monkeypatch.patch_llava_onevision("h2o")
+
+
+def test_qwen2vl_helpers():
+    from retake import qwen2_vl as g
+    me = types.SimpleNamespace(config=types.SimpleNamespace(video_token_id=7, longvideo_kwargs={"chunked_prefill_frames": 32},
+                                                            vision_config=types.SimpleNamespace(spatial_merge_size=2, temporal_patch_size=2)))
+    ids = torch.tensor([[1, 2, 7, 7, 7, 7, 3, 7, 7, 4]])
+    assert g.retake_Qwen2VLForConditionalGeneration_segment_input_ids(me, ids) == [
+        (0, 2, "text"), (2, 6, "video"), (6, 7, "text"), (7, 9, "video"), (9, 10, "text")]
+    thw = torch.tensor([[1024, 32, 32]])
+    assert g.retake_Qwen2VLForConditionalGeneration_get_chunk_size(me, me.config, thw) == 4096      # 2048 frames @448px
+    assert g.retake_Qwen2VLForConditionalGeneration_get_chunk_size(me, me.config, torch.tensor([[4, 32, 32]])) == 512
+    me.config.longvideo_kwargs = {}
+    assert g.retake_Qwen2VLForConditionalGeneration_get_chunk_size(me, me.config, thw) is None
+    # M-RoPE ids: 2 text, video T=2 H=2 W=2 (merged), 3 text
+    ids = torch.tensor([[1, 2] + [7] * 8 + [3, 4, 5]])
+    pos, delta = g.mrope_position_ids(ids, 7, torch.tensor([[2, 4, 4]]), 2)
+    assert pos[0, 0].tolist() == [0, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 5, 6]
+    assert pos[1, 0].tolist() == [0, 1, 2, 2, 3, 3, 2, 2, 3, 3, 4, 5, 6]
+    assert pos[2, 0].tolist() == [0, 1, 2, 3, 2, 3, 2, 3, 2, 3, 4, 5, 6]
+    assert int(delta) == 7 - 13
+    # visual compression off: everything passes through, no mask
+    me.config.longvideo_kwargs = {"visual_compression": False}
+    out = g.retake_Qwen2VLForConditionalGeneration_compress_video_tokens(me, input_ids=ids, attention_mask=None,
+                                                                         video_embeds=torch.zeros(8, 4), position_ids=pos,
+                                                                         video_grid_thw=torch.tensor([[2, 4, 4]]))
+    assert out[0] is ids and out[4] is pos and out[6] is None
+
+
+def test_llava_helpers():
+    from retake import llava_onevision as g
+    me = types.SimpleNamespace(config=types.SimpleNamespace(video_token_index=9, longvideo_kwargs={"chunked_prefill_frames": 32},
+                                                            vision_config=types.SimpleNamespace(patch_size=14, image_size=384)))
+    px = torch.zeros(1, 64, 3, 384, 384, dtype=torch.bfloat16)
+    assert g.retake_LlavaOnevisionForConditionalGeneration_get_chunk_size(me, me.config, px) == 32 * 14 * 14   # 6272
+    ids = torch.tensor([[9, 9, 1, 2]])
+    assert g.retake_LlavaOnevisionForConditionalGeneration_segment_input_ids(me, ids) == [(0, 2, "video"), (2, 4, "text")]
