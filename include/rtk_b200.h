@@ -132,6 +132,13 @@ int rtk_pivot_compact(const void* k, const void* v, int64_t KVH, int64_t L, int6
                       void* k_out, void* v_out, int64_t out_stride_h,
                       const int64_t* pos, int n_pos, int64_t* pos_out, int reforge, void* stream);
 
+/* Up to four strided bf16 [heads, rows, D] block copies in one launch: the in-place cache append of K and V
+ * (DynamicCache.update's torch.cat, longvideo_cache.py:238) and the write of the kept rows over the previous chunk
+ * (longvideo_cache.py:313-318).  Arrays have n_jobs entries; strides in elements. */
+int rtk_kv_block_copy(int n_jobs, const void* const* src, void* const* dst, const int64_t* heads, const int64_t* rows,
+                      const int64_t* src_stride_h, const int64_t* src_stride_l, const int64_t* dst_stride_h,
+                      const int64_t* dst_stride_l, int64_t D, void* stream);
+
 /* cos/sin tables of one chunk from the rotary module's inv_freq (fp32 [D/2]); replaces the two
  * `rotary_emb_fn(x, position_ids)` calls of longvideo_cache.py:249,298 plus the mrope row selection of :67-73 when
  * the module is a stock HF rotary embedding with a static inv_freq:

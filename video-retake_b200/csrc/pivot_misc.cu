@@ -61,14 +61,34 @@ pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
         uint4 ol4, oh4;
         __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(&ol4);
         __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&oh4);
+        // cos/sin of the 8 + 8 channels: one 16-byte load each when a vector does not straddle an mrope block
+        const int rowa0 = rope_pos_row(p, c0), rowa1 = rope_pos_row(p, c0 + 7);
+        const int rowb0 = rope_pos_row(p, c0 + half), rowb1 = rope_pos_row(p, c0 + half + 7);
+        uint4 ca4, sa4, cb4, sb4;
+        __nv_bfloat16* cav = reinterpret_cast<__nv_bfloat16*>(&ca4);
+        __nv_bfloat16* sav = reinterpret_cast<__nv_bfloat16*>(&sa4);
+        __nv_bfloat16* cbv = reinterpret_cast<__nv_bfloat16*>(&cb4);
+        __nv_bfloat16* sbv = reinterpret_cast<__nv_bfloat16*>(&sb4);
+        if (rowa0 == rowa1 && rowb0 == rowb1) {
+            const size_t ia = ((size_t)rowa0 * p.L + l) * p.D + c0, ib = ((size_t)rowb0 * p.L + l) * p.D + c0 + half;
+            ca4 = __ldg(reinterpret_cast<const uint4*>(cos_t + ia));
+            sa4 = __ldg(reinterpret_cast<const uint4*>(sin_t + ia));
+            cb4 = __ldg(reinterpret_cast<const uint4*>(cos_t + ib));
+            sb4 = __ldg(reinterpret_cast<const uint4*>(sin_t + ib));
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int ca = c0 + e, cb = c0 + e + half;
+                const size_t ia = ((size_t)rope_pos_row(p, ca) * p.L + l) * p.D + ca;
+                const size_t ib = ((size_t)rope_pos_row(p, cb) * p.L + l) * p.D + cb;
+                cav[e] = cos_t[ia]; sav[e] = sin_t[ia]; cbv[e] = cos_t[ib]; sbv[e] = sin_t[ib];
+            }
+        }
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const int ca = c0 + e, cb = c0 + e + half;
-            const size_t ia = ((size_t)rope_pos_row(p, ca) * p.L + l) * p.D + ca;
-            const size_t ib = ((size_t)rope_pos_row(p, cb) * p.L + l) * p.D + cb;
             const float xa = __bfloat162float(xl[e]), xb = __bfloat162float(xh[e]);
-            const float cosa = __bfloat162float(cos_t[ia]), sina = __bfloat162float(sin_t[ia]);
-            const float cosb = __bfloat162float(cos_t[ib]), sinb = __bfloat162float(sin_t[ib]);
+            const float cosa = __bfloat162float(cav[e]), sina = __bfloat162float(sav[e]);
+            const float cosb = __bfloat162float(cbv[e]), sinb = __bfloat162float(sbv[e]);
             // rotate_half: lower half pairs with -x[c + D/2], upper half with +x[c - D/2]
             const float ta = round_bf16(xa * cosa), ra = round_bf16(-xb * sina);
             const float tb = round_bf16(xb * cosb), rb = round_bf16(xa * sinb);
@@ -222,6 +242,35 @@ pivot_compact_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* _
         const size_t dof = (size_t)h * p.out_stride_h + (size_t)j * p.D + (size_t)c * 8;
         if (k) *reinterpret_cast<uint4*>(k_out + dof) = __ldg(reinterpret_cast<const uint4*>(k + so));
         if (v) *reinterpret_cast<uint4*>(v_out + dof) = __ldg(reinterpret_cast<const uint4*>(v + so));
+    }
+}
+
+// up to four strided [heads, rows, D] block copies in ONE launch (cache append of K and V + the deferred overwrite of the
+// previous layer's chunk head by its kept rows); replaces four torch copy_ launches per update
+struct CopyJobs {
+    int n;
+    const __nv_bfloat16* src[4];
+    __nv_bfloat16* dst[4];
+    int heads[4], rows[4];
+    long long src_stride_h[4], src_stride_l[4], dst_stride_h[4], dst_stride_l[4];
+    long long vec_end[4];          // exclusive prefix of 16-byte vectors over the jobs
+    int D;
+};
+
+__global__ void __launch_bounds__(256)
+kv_block_copy_kernel(CopyJobs j) {
+    const int vpr = j.D >> 3;
+    const long long total = j.vec_end[j.n - 1];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int k = 0;
+        while (i >= j.vec_end[k]) ++k;
+        const long long li = i - (k ? j.vec_end[k - 1] : 0);
+        const int c = (int)(li % vpr);
+        const long long hr = li / vpr;
+        const int r = (int)(hr % j.rows[k]);
+        const int h = (int)(hr / j.rows[k]);
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(j.src[k] + h * j.src_stride_h[k] + r * j.src_stride_l[k] + c * 8));
+        *reinterpret_cast<uint4*>(j.dst[k] + h * j.dst_stride_h[k] + r * j.dst_stride_l[k] + c * 8) = v;
     }
 }
 
@@ -410,5 +459,36 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
                             a->out_stride_h, D, stream);
         if (rc) return rc;
     }
+    return 0;
+}
+
+extern "C" int rtk_kv_block_copy(int n_jobs, const void* const* src, void* const* dst, const int64_t* heads, const int64_t* rows,
+                                 const int64_t* src_stride_h, const int64_t* src_stride_l, const int64_t* dst_stride_h,
+                                 const int64_t* dst_stride_l, int64_t D, void* stream) {
+    if (n_jobs < 1 || n_jobs > 4 || !src || !dst || !heads || !rows || D < 8) return RTK_E_BADARG;
+    if (D % 8 != 0) return RTK_E_UNSUPPORTED;
+    CopyJobs j;
+    j.n = n_jobs;
+    j.D = (int)D;
+    long long acc = 0;
+    for (int k = 0; k < n_jobs; ++k) {
+        if (!src[k] || !dst[k] || heads[k] < 1 || rows[k] < 0) return RTK_E_BADARG;
+        if ((((uintptr_t)src[k] | (uintptr_t)dst[k]) & 15u) != 0) return RTK_E_ALIGN;
+        if ((src_stride_h[k] | src_stride_l[k] | dst_stride_h[k] | dst_stride_l[k]) % 8 != 0) return RTK_E_ALIGN;
+        j.src[k] = (const __nv_bfloat16*)src[k];
+        j.dst[k] = (__nv_bfloat16*)dst[k];
+        j.heads[k] = (int)heads[k];
+        j.rows[k] = (int)rows[k];
+        j.src_stride_h[k] = src_stride_h[k]; j.src_stride_l[k] = src_stride_l[k];
+        j.dst_stride_h[k] = dst_stride_h[k]; j.dst_stride_l[k] = dst_stride_l[k];
+        acc += heads[k] * rows[k] * (D / 8);
+        j.vec_end[k] = acc;
+    }
+    for (int k = n_jobs; k < 4; ++k) j.vec_end[k] = acc;
+    if (acc == 0) return 0;
+    long long grid = (acc + 255) / 256;
+    if (grid > 148 * 8) grid = 148 * 8;
+    kv_block_copy_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(j);
+    RTK_CHECK_LAUNCH();
     return 0;
 }

@@ -47,6 +47,7 @@ def lib() -> C.CDLL:
         "rtk_pivot_rope_tables": ([p, i32, i64, i64, p, p, f32, p, p, p], C.c_int),
         "rtk_pivot_update_workspace_bytes": ([i64, i64, i64, i64], sz),
         "rtk_pivot_update": ([p, p], C.c_int),
+        "rtk_kv_block_copy": ([i32, p, p, p, p, p, p, p, p, i64, p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)            # AttributeError here == header and library disagree
@@ -60,7 +61,7 @@ def lib() -> C.CDLL:
 EXPORTS = ("rtk_version", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
            "rtk_dpselect_gather", "rtk_gather_rows", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
            "rtk_pivot_select", "rtk_pivot_compact", "rtk_pivot_rope_tables", "rtk_pivot_update_workspace_bytes",
-           "rtk_pivot_update")
+           "rtk_pivot_update", "rtk_kv_block_copy")
 
 
 def check(rc: int, what: str) -> None:

@@ -172,6 +172,28 @@ def pivot_compact(key_states: torch.Tensor, value_states: torch.Tensor, keep_idx
     return k_out, v_out, pos_out
 
 
+def _block_copy(jobs) -> None:
+    """``[(src[1, heads, rows, D], dst[1, heads, rows, D]), ...]`` strided bf16 block copies, four per launch"""
+    for i in range(0, len(jobs), 4):
+        part = jobs[i:i + 4]
+        n = len(part)
+        srcs, dsts = [], []
+        for a, b in part:
+            if a.stride(3) != 1 or a.data_ptr() % 16 or a.stride(1) % 8 or a.stride(2) % 8:
+                a = a.contiguous()
+            srcs.append(a)
+            dsts.append(b)
+        P, I = C.c_void_p * n, C.c_int64 * n
+        dev = dsts[0].device
+        with torch.cuda.device(dev):
+            N.check(N.lib().rtk_kv_block_copy(
+                n, P(*[t.data_ptr() for t in srcs]), P(*[t.data_ptr() for t in dsts]),
+                I(*[t.shape[1] for t in srcs]), I(*[t.shape[2] for t in srcs]),
+                I(*[t.stride(1) for t in srcs]), I(*[t.stride(2) for t in srcs]),
+                I(*[t.stride(1) for t in dsts]), I(*[t.stride(2) for t in dsts]),
+                srcs[0].shape[3], N.stream_ptr(dev)), "rtk_kv_block_copy")
+
+
 class _UpdateArgs(C.Structure):
     """mirror of ``rtk_pivot_update_args`` (include/rtk_b200.h)"""
     _fields_ = [("q", C.c_void_p), ("H", C.c_int64), ("q_stride_h", C.c_int64), ("q_stride_l", C.c_int64),
@@ -275,14 +297,20 @@ class PivotKVLayer(DynamicLayer):
     def get_seq_length(self) -> int:
         return self._len if self.is_initialized else 0
 
-    def flush(self):
+    def pending_jobs(self):
+        """copy jobs that settle the deferred overwrite (and forget it)"""
         p = self._pending
-        if p is not None:
-            self._pending = None
-            kk, vv, start = p
-            n = kk.shape[2]
-            self._kbuf[:, :, start:start + n].copy_(kk)
-            self._vbuf[:, :, start:start + n].copy_(vv)
+        if p is None:
+            return []
+        self._pending = None
+        kk, vv, start = p
+        n = kk.shape[2]
+        return [(kk, self._kbuf[:, :, start:start + n]), (vv, self._vbuf[:, :, start:start + n])]
+
+    def flush(self):
+        jobs = self.pending_jobs()
+        if jobs:
+            _block_copy(jobs)
 
     def _reserve(self, heads, n, d):
         cap = 0 if self._kbuf is None else self._kbuf.shape[2]
@@ -296,20 +324,28 @@ class PivotKVLayer(DynamicLayer):
             vb[:, :, :self._len].copy_(self._vbuf[:, :, :self._len])
         self._kbuf, self._vbuf = kb, vb
 
-    def update(self, key_states, value_states, *args, **kwargs):
-        """append in place, return views ``[past | new]``"""
+    def append_jobs(self, key_states, value_states):
+        """reserve room, advance the length and return (copy jobs, keys view, values view) for ``[past | new]``"""
         if not self.is_initialized:
             self.lazy_initialization(key_states, value_states)
-        self.flush()
         _, heads, n_new, d = key_states.shape
         p = self._len
-        self._reserve(heads, p + n_new, d)
-        self._kbuf[:, :, p:p + n_new].copy_(key_states)
-        self._vbuf[:, :, p:p + n_new].copy_(value_states)
+        cap = 0 if self._kbuf is None else self._kbuf.shape[2]
+        if p + n_new > cap:
+            self.flush()                                  # the old buffer is about to be copied: settle it first
+            self._reserve(heads, p + n_new, d)
+        jobs = [(key_states, self._kbuf[:, :, p:p + n_new]), (value_states, self._vbuf[:, :, p:p + n_new])]
         self._len = p + n_new
         self._keys_view = self._kbuf[:, :, :self._len]
         self._values_view = self._vbuf[:, :, :self._len]
-        return self._keys_view, self._values_view
+        return jobs, self._keys_view, self._values_view
+
+    def update(self, key_states, value_states, *args, **kwargs):
+        """append in place, return views ``[past | new]``"""
+        jobs = self.pending_jobs()
+        more, k_all, v_all = self.append_jobs(key_states, value_states)
+        _block_copy(jobs + more)
+        return k_all, v_all
 
     def replace_tail(self, n_tail, kept_k, kept_v):
         """the last ``n_tail`` rows become ``kept_*`` - length changes now, bytes move at the next flush"""
@@ -507,13 +543,15 @@ class PivotKVCache(DynamicCache):
         cache_kwargs = cache_kwargs if cache_kwargs is not None else {}
         position_ids = cache_kwargs.pop("position_ids", None)
 
-        # the previous layer's attention is on the stream by now: its kept rows may land
-        self.flush()
-        # 1) this chunk attends to everything: [past | chunk] is what the caller gets back
+        # 1) this chunk attends to everything: [past | chunk] is what the caller gets back.  The previous layer's
+        #    attention is on the stream by now, so its kept rows may land: both go out as ONE block-copy launch.
         while len(self.layers) <= layer_idx:
             self.layers.append(PivotKVLayer())
         layer = self.layers[layer_idx]
-        key_states_output, value_states_output = layer.update(key_states, value_states)
+        dirty, self._dirty = self._dirty, []
+        jobs = [j for l in dirty for j in l.pending_jobs()]
+        more, key_states_output, value_states_output = layer.append_jobs(key_states, value_states)
+        _block_copy(jobs + more)
 
         if self.kvcache_compression:
             query_states = cache_kwargs.pop("query_states")
