@@ -361,3 +361,25 @@ def test_cache_storage_semantics():
     assert ko3.shape[2] == 13 and cache.get_seq_length(0) == 13
     cache.after_forward()
     assert cache.num_evicted_tokens == [L, L // 2]
+
+
+@pytest.mark.parametrize("reforge", [False, True])
+def test_update_single_token_tail_chunk(reforge):
+    """LLaVA-Video has frames * 196 + 1 video tokens, so the last prefill chunk can be ONE token: keep = max(1, int(r)) = 1"""
+    lc = _lc()
+    H, KVH, D = 28, 4, 128
+    rot = TableRotary(D, mrope=False)
+    rot.inv_freq = rot.inv_freq.cuda()
+    cache = lc.PivotKVCache(_cfg(H, KVH, D, 1, 0.25, reforge))
+    total = 0
+    for L, base in ((256, 0), (1, 256)):
+        q, k, v = qkv(H, KVH, L, D, 1.0, seed=L)
+        pos = (torch.arange(L, device="cuda") + (int(cache.get_prev_temporal_idx(0)) + 1 if reforge else base))[None]
+        cache.keypatches_mask_chunk = torch.zeros(L, dtype=torch.bool, device="cuda")
+        ko, vo = cache.update(k, v, 0, {"query_states": q, "position_ids": pos, "rotary_emb": rot, "mrope_section": None})
+        assert ko.shape[2] == total + L and torch.equal(ko[:, :, total:], k)
+        total += max(1, int(0.25 * L))
+        assert cache.get_seq_length(0) == total
+    assert cache.last_keep_indices.tolist() == [0] and cache.layers[0].keys.shape[2] == 65
+    if reforge:
+        assert cache.position_cache[0].shape == (1, 65)

@@ -10,6 +10,11 @@ namespace rtk {
 struct RopeParams {
     int heads, L, D, n_pos, forward;
     long long stride_h, stride_l, out_stride_h, out_stride_l;
+    // optional second tensor handled by the same launch (k next to q): heads [heads, heads + heads2)
+    int heads2;
+    const __nv_bfloat16* x2;
+    __nv_bfloat16* out2;
+    long long stride_h2, stride_l2, out_stride_h2, out_stride_l2;
     int bound[6];            // exclusive channel boundaries of the six mrope blocks (sections * 2)
     float inv_scale2;
 };
@@ -45,15 +50,17 @@ pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
                   const __nv_bfloat16* __restrict__ sin_t, __nv_bfloat16* __restrict__ out, RopeParams p) {
     const int half = p.D >> 1;
     const int vec_per_row = half >> 3;
-    const long long total = (long long)p.heads * p.L * vec_per_row;
+    const long long total = (long long)(p.heads + p.heads2) * p.L * vec_per_row;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int v = (int)(i % vec_per_row);
         const long long hl = i / vec_per_row;
         const int l = (int)(hl % p.L);
         const int h = (int)(hl / p.L);
         const int c0 = v * 8;
-        const __nv_bfloat16* src = x + h * p.stride_h + l * p.stride_l;
-        __nv_bfloat16* dst = out + h * p.out_stride_h + l * p.out_stride_l;
+        const bool second = h >= p.heads;
+        const __nv_bfloat16* src = second ? p.x2 + (h - p.heads) * p.stride_h2 + l * p.stride_l2 : x + h * p.stride_h + l * p.stride_l;
+        __nv_bfloat16* dst = second ? p.out2 + (h - p.heads) * p.out_stride_h2 + l * p.out_stride_l2
+                                    : out + h * p.out_stride_h + l * p.out_stride_l;
         uint4 lo4 = *reinterpret_cast<const uint4*>(src + c0);
         uint4 hi4 = *reinterpret_cast<const uint4*>(src + c0 + half);
         const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(&lo4);
@@ -200,6 +207,7 @@ pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int 
 struct CompactParams {
     int KVH, L, D, keep, n_pos, reforge;
     long long stride_h, stride_l, out_stride_h;
+    long long v_stride_h, v_stride_l;
     float ratio;              // fp32(keep / L)
 };
 
@@ -238,10 +246,12 @@ pivot_compact_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* _
         const long long hj = i / vec_per_row;
         const int j = (int)(hj % p.keep);
         const int h = (int)(hj / p.keep);
-        const size_t so = (size_t)h * p.stride_h + (size_t)keep_idx[j] * p.stride_l + (size_t)c * 8;
+        const int src_row = keep_idx[j];
+        const size_t so = (size_t)h * p.stride_h + (size_t)src_row * p.stride_l + (size_t)c * 8;
+        const size_t sv = (size_t)h * p.v_stride_h + (size_t)src_row * p.v_stride_l + (size_t)c * 8;
         const size_t dof = (size_t)h * p.out_stride_h + (size_t)j * p.D + (size_t)c * 8;
         if (k) *reinterpret_cast<uint4*>(k_out + dof) = __ldg(reinterpret_cast<const uint4*>(k + so));
-        if (v) *reinterpret_cast<uint4*>(v_out + dof) = __ldg(reinterpret_cast<const uint4*>(v + so));
+        if (v) *reinterpret_cast<uint4*>(v_out + dof) = __ldg(reinterpret_cast<const uint4*>(v + sv));
     }
 }
 
@@ -310,6 +320,8 @@ extern "C" int rtk_pivot_rope(const void* x, int64_t heads, int64_t L, int64_t D
     p.heads = (int)heads; p.L = (int)L; p.D = (int)D; p.n_pos = n_pos; p.forward = forward;
     p.stride_h = stride_h; p.stride_l = stride_l; p.out_stride_h = out_stride_h; p.out_stride_l = out_stride_l;
     p.inv_scale2 = inv_scale2;
+    p.heads2 = 0; p.x2 = nullptr; p.out2 = nullptr;
+    p.stride_h2 = p.stride_l2 = p.out_stride_h2 = p.out_stride_l2 = 0;
     int acc = 0;
     for (int i = 0; i < 6; ++i) {
         acc += (n_pos == 3) ? mrope_section_host[i % 3] : 0;
@@ -338,19 +350,31 @@ extern "C" int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L,
     return 0;
 }
 
+static int compact_kv(const void* k, const void* v, int64_t KVH, int64_t L, int64_t D, int64_t stride_h, int64_t stride_l,
+                      int64_t v_stride_h, int64_t v_stride_l, const int32_t* keep_idx, int64_t keep, void* k_out, void* v_out,
+                      int64_t out_stride_h, const int64_t* pos, int n_pos, int64_t* pos_out, int reforge, void* stream);
+
 extern "C" int rtk_pivot_compact(const void* k, const void* v, int64_t KVH, int64_t L, int64_t D, int64_t stride_h,
                                  int64_t stride_l, const int32_t* keep_idx, int64_t keep, void* k_out, void* v_out,
                                  int64_t out_stride_h, const int64_t* pos, int n_pos, int64_t* pos_out, int reforge,
                                  void* stream) {
+    return compact_kv(k, v, KVH, L, D, stride_h, stride_l, stride_h, stride_l, keep_idx, keep, k_out, v_out, out_stride_h, pos,
+                      n_pos, pos_out, reforge, stream);
+}
+
+static int compact_kv(const void* k, const void* v, int64_t KVH, int64_t L, int64_t D, int64_t stride_h, int64_t stride_l,
+                      int64_t v_stride_h, int64_t v_stride_l, const int32_t* keep_idx, int64_t keep, void* k_out, void* v_out,
+                      int64_t out_stride_h, const int64_t* pos, int n_pos, int64_t* pos_out, int reforge, void* stream) {
     if ((!k && !v) || !keep_idx || (k && !k_out) || (v && !v_out) || KVH < 1 || L < 1 || D < 8 || keep < 1 || keep > L)
         return RTK_E_BADARG;
     if (pos && (!pos_out || n_pos < 1)) return RTK_E_BADARG;
     if (D % 8 != 0) return RTK_E_UNSUPPORTED;
     if ((((uintptr_t)k | (uintptr_t)v | (uintptr_t)k_out | (uintptr_t)v_out) & 15u) != 0) return RTK_E_ALIGN;   // NULL passes
-    if ((stride_h | stride_l | out_stride_h) % 8 != 0) return RTK_E_ALIGN;
+    if ((stride_h | stride_l | v_stride_h | v_stride_l | out_stride_h) % 8 != 0) return RTK_E_ALIGN;
     CompactParams p;
     p.KVH = (int)KVH; p.L = (int)L; p.D = (int)D; p.keep = (int)keep; p.n_pos = n_pos; p.reforge = reforge;
     p.stride_h = stride_h; p.stride_l = stride_l; p.out_stride_h = out_stride_h;
+    p.v_stride_h = v_stride_h; p.v_stride_l = v_stride_l;
     p.ratio = (float)((double)keep / (double)L);
     const long long total = KVH * keep * (D / 8);
     long long grid = (total + 255) / 256;
@@ -371,6 +395,8 @@ extern "C" int rtk_pivot_rope_tables(const int64_t* pos, int n_pos, int64_t L, i
     RopeParams p;
     p.heads = 1; p.L = (int)L; p.D = (int)D; p.n_pos = n_pos; p.forward = 0;
     p.stride_h = p.stride_l = p.out_stride_h = p.out_stride_l = 0;
+    p.heads2 = 0; p.x2 = nullptr; p.out2 = nullptr;
+    p.stride_h2 = p.stride_l2 = p.out_stride_h2 = p.out_stride_l2 = 0;
     p.inv_scale2 = 1.0f;
     int acc = 0;
     for (int i = 0; i < 6; ++i) {
@@ -382,6 +408,33 @@ extern "C" int rtk_pivot_rope_tables(const int64_t* pos, int n_pos, int64_t L, i
     if (grid > 148 * 8) grid = 148 * 8;
     pivot_rope_table_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
         (const long long*)pos, inv_freq, p, attention_scaling, (__nv_bfloat16*)cos_out, (__nv_bfloat16*)sin_out);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+// un-rotate q and k with pre-selected [L, D] tables in ONE launch
+static int rope_qk_reverse(const void* q, int64_t H, int64_t qsh, int64_t qsl, const void* k, int64_t KVH, int64_t ksh, int64_t ksl,
+                           int64_t L, int64_t D, const void* cos, const void* sin, int n_pos, const int32_t* sec, float inv_scale2,
+                           void* qu, void* ku, cudaStream_t st) {
+    if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)qu | (uintptr_t)ku) & 15u) != 0) return RTK_E_ALIGN;
+    if ((qsh | qsl | ksh | ksl) % 8 != 0 || D % 16 != 0) return RTK_E_ALIGN;
+    RopeParams p;
+    p.heads = (int)H; p.L = (int)L; p.D = (int)D; p.n_pos = n_pos; p.forward = 0;
+    p.stride_h = qsh; p.stride_l = qsl; p.out_stride_h = L * D; p.out_stride_l = D;
+    p.heads2 = (int)KVH; p.x2 = (const __nv_bfloat16*)k; p.out2 = (__nv_bfloat16*)ku;
+    p.stride_h2 = ksh; p.stride_l2 = ksl; p.out_stride_h2 = L * D; p.out_stride_l2 = D;
+    p.inv_scale2 = inv_scale2;
+    int acc = 0;
+    for (int i = 0; i < 6; ++i) {
+        acc += (n_pos == 3 && sec) ? sec[i % 3] : 0;
+        p.bound[i] = acc;
+    }
+    if (n_pos == 3 && acc != D) return RTK_E_UNSUPPORTED;
+    const long long total = (H + KVH) * L * (D / 16);
+    long long grid = (total + 255) / 256;
+    if (grid > 148 * 16) grid = 148 * 16;
+    pivot_rope_kernel<<<(unsigned)grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin,
+                                                      (__nv_bfloat16*)qu, p);
     RTK_CHECK_LAUNCH();
     return 0;
 }
@@ -425,9 +478,8 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
         } else if (!c || !s) {
             return RTK_E_BADARG;
         }
-        rc = rtk_pivot_rope(q, H, L, D, qsh, qsl, c, s, n_pos_tab, sec, a->inv_scale2, 0, qu, L * D, D, stream);
-        if (rc) return rc;
-        rc = rtk_pivot_rope(k, KVH, L, D, ksh, ksl, c, s, n_pos_tab, sec, a->inv_scale2, 0, ku, L * D, D, stream);
+        rc = rope_qk_reverse(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, c, s, n_pos_tab, sec, a->inv_scale2, qu, ku,
+                             (cudaStream_t)stream);
         if (rc) return rc;
         q = qu; k = ku; qsh = ksh = L * D; qsl = ksl = D;
     }
@@ -438,19 +490,10 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
     if (a->skip_select) return 0;
     rc = rtk_pivot_select(a->head_scores, KVH, L, a->keymask, a->keep, a->keep_idx, nullptr, stream);
     if (rc) return rc;
-    if (!a->reforge && a->v_stride_h == a->k_stride_h_in && a->v_stride_l == a->k_stride_l_in) {
-        rc = rtk_pivot_compact(k, a->v, KVH, L, D, ksh, ksl, a->keep_idx, a->keep, a->k_out, a->v_out, a->out_stride_h, a->pos,
-                               a->pos ? a->n_pos : 0, a->pos_out, 0, stream);
-        if (rc) return rc;
-    } else {
-        // K comes from the un-rotated copy (or has other strides than V): gather K + positions, then V alone
-        rc = rtk_pivot_compact(k, nullptr, KVH, L, D, ksh, ksl, a->keep_idx, a->keep, a->k_out, nullptr, a->out_stride_h, a->pos,
-                               a->pos ? a->n_pos : 0, a->pos_out, a->reforge, stream);
-        if (rc) return rc;
-        rc = rtk_pivot_compact(nullptr, a->v, KVH, L, D, a->v_stride_h, a->v_stride_l, a->keep_idx, a->keep, nullptr, a->v_out,
-                               a->out_stride_h, nullptr, 0, nullptr, 0, stream);
-        if (rc) return rc;
-    }
+    // K (possibly the un-rotated copy) and V (caller's strides) + positions in one launch
+    rc = compact_kv(k, a->v, KVH, L, D, ksh, ksl, a->v_stride_h, a->v_stride_l, a->keep_idx, a->keep, a->k_out, a->v_out,
+                    a->out_stride_h, a->pos, a->pos ? a->n_pos : 0, a->pos_out, a->reforge, stream);
+    if (rc) return rc;
     if (fused_tables) {
         const int32_t* sec = a->n_pos == 3 ? a->mrope_section : nullptr;
         rc = rtk_pivot_rope_tables(a->pos_out, a->n_pos, a->keep, D, a->inv_freq, sec, a->attention_scaling, cos2, sin2, stream);
