@@ -95,6 +95,8 @@ def cache_config(s):
 
 def synth_host(s, pool, seed):
     """pinned host inputs: scene-structured embeddings + a pool of Q/K/V sets in the attention layout [1, L, heads, D]"""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // world))      # ranks share the host cores while generating
     g = torch.Generator().manual_seed(seed)
     x = torch.empty(s.T, s.N, s.C, dtype=torch.bfloat16)
     t = 0
