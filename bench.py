@@ -28,7 +28,8 @@ for p in (ROOT, os.path.join(ROOT, "video-retake_b200"), os.path.join(ROOT, "tes
     if p not in sys.path:
         sys.path.insert(0, p)
 
-os.environ.setdefault("NCCL_DEBUG", "WARN")        # keep stdout to the one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"                   # keep stdout to the one JSON line
 
 import torch  # noqa: E402
 

@@ -90,6 +90,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, "
+        "%32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, "
+        "%48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]),
+          "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]),
+          "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]),
+          "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]),
+          "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+        : "r"(taddr)
+        : "memory");
+}
 // wait for the outstanding TMEM loads; the registers are listed so that no use of them can be scheduled above it
 __device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
@@ -188,8 +206,14 @@ __device__ __forceinline__ float logit_chain1(float acc, float inv) { return rou
 #ifndef RTK_SCORE_X16
 #define RTK_SCORE_X16 0        // 16-column TMEM loads, double buffered (1) vs 32-column blocking loads (0)
 #endif
+#ifndef RTK_SCORE_X64
+#define RTK_SCORE_X64 1          // one 64-column TMEM load per tile half (default; -2 % vs two 32-column loads)
+#endif
+#ifndef RTK_SCORE_X32DB
+#define RTK_SCORE_X32DB 0
+#endif
 #ifndef RTK_SCORE_FHADD
-#define RTK_SCORE_FHADD 0      // pass 2: accumulate bf16 halves with FHADD.BF16 (1) vs widen + packed fp32 add (0)
+#define RTK_SCORE_FHADD 1      // pass 2: accumulate bf16 halves with FHADD.BF16 (1, default) vs widen + packed fp32 add (0)
 #endif
 #ifndef RTK_SCORE_LAZY
 #define RTK_SCORE_LAZY 0       // pass 1: rescale only when some lane's maximum grew (1) vs every step (0)
@@ -466,6 +490,22 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                     if (j < 3) tmem_ld16(taddr + (j + 1) * 16, rn);
                     softmax_cols<PASS, 16>(r, j * 16, valid, st, cq, inv, inv2, l2e2);
                     if (j < 3) tmem_ld_wait16(rn);
+                }
+#elif RTK_SCORE_X64
+                {
+                    uint32_t r[64];
+                    tmem_ld64(taddr, r);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 64>(r, 0, valid, st, cq, inv, inv2, l2e2);
+                }
+#elif RTK_SCORE_X32DB
+                {   // both 32-column loads issued up front: the second is in flight while the first half is computed
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(taddr, ra);
+                    tmem_ld32(taddr + 32, rb);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 32>(ra, 0, valid, st, cq, inv, inv2, l2e2);
+                    softmax_cols<PASS, 32>(rb, 32, valid, st, cq, inv, inv2, l2e2);
                 }
 #else
 #pragma unroll 1
