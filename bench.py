@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=2048)
+    ap.add_argument("--shape", default="qwen2vl", choices=["qwen2vl", "llava"],
+                    help="qwen2vl: Qwen2-VL-7B @448px (headline); llava: LLaVA-Video-Qwen2-7B, SigLIP-so400m grid (config 4)")
     ap.add_argument("--visual-ratio", type=float, default=1.0)
     ap.add_argument("--kv-ratio", type=float, default=-1.0, help="-1: dynamic, 32000 / video tokens (shipped recipe)")
     ap.add_argument("--no-reforge", action="store_true")
@@ -55,25 +57,42 @@ def parse():
 
 
 class Shape:
-    """Qwen2-VL-7B shape at 448x448."""
+    """Qwen2-VL-7B shape at 448x448, or LLaVA-Video-Qwen2-7B with the SigLIP-so400m token grid."""
 
     def __init__(self, a):
+        self.name = a.shape
         self.frames = a.frames
-        self.T = a.frames // 2            # temporal_patch_size 2
-        self.N, self.C = 256, 3584
         self.H, self.KVH, self.D = 28, 4, 128
         self.layers = a.layers
-        self.L = min(32, self.T) * 1024 // 8            # chunked_prefill_frames 32 -> 4096 tokens
-        self.t = max(1, round(a.visual_ratio * self.T))
-        self.tokens = self.t * self.N
-        self.chunks = (self.tokens + self.L - 1) // self.L
-        self.kv_ratio = a.kv_ratio if a.kv_ratio > 0 else min(1.0, 32000 / self.tokens)
-        self.keep = max(1, int(self.kv_ratio * self.L))
         self.reforge = not a.no_reforge
-        self.mrope = [16, 24, 24]
+        if a.shape == "qwen2vl":
+            self.T = a.frames // 2            # temporal_patch_size 2
+            self.N, self.C = 256, 3584        # DPSelect runs on the LLM-side embeddings
+            self.tok_per_grid = 256
+            self.L = min(32, self.T) * 1024 // 8            # chunked_prefill_frames 32 -> 4096 tokens
+            self.mrope, budget = [16, 24, 24], 32000
+        else:
+            self.T = a.frames
+            self.N, self.C = 729, 1152        # DPSelect runs on the SigLIP features before the projector
+            self.tok_per_grid = 196           # after projector + 2x bilinear pooling
+            self.L = min(32, self.T) * 196    # 6272
+            self.mrope, budget = None, 40000
+        self.t = max(1, round(a.visual_ratio * self.T))
+        self.tokens = self.t * self.tok_per_grid           # (the newline slot is dropped with visual compression on)
+        self.chunks = (self.tokens + self.L - 1) // self.L
+        self.kv_ratio = a.kv_ratio if a.kv_ratio > 0 else min(1.0, budget / self.tokens)
+        self.keep = max(1, int(self.kv_ratio * self.L))
 
 
-def make_rotary(device):
+def make_rotary(device, shape="qwen2vl"):
+    if shape == "llava":
+        from transformers.models.qwen2.configuration_qwen2 import Qwen2Config
+        from transformers.models.qwen2.modeling_qwen2 import Qwen2RotaryEmbedding
+        tc = Qwen2Config(hidden_size=3584, num_attention_heads=28, num_key_value_heads=4, num_hidden_layers=28,
+                         max_position_embeddings=32768,
+                         rope_parameters={"rope_type": "yarn", "factor": 4.0, "beta_fast": 32.0, "beta_slow": 1.0,
+                                          "rope_theta": 1e6, "original_max_position_embeddings": 32768})
+        return Qwen2RotaryEmbedding(tc).to(device)
     from transformers.models.qwen2_vl.configuration_qwen2_vl import Qwen2VLTextConfig
     from transformers.models.qwen2_vl.modeling_qwen2_vl import Qwen2VLRotaryEmbedding
     tc = Qwen2VLTextConfig(hidden_size=3584, num_attention_heads=28, num_key_value_heads=4, num_hidden_layers=28,
@@ -155,15 +174,15 @@ def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer=None):
         ss, ee = c * s.L, min((c + 1) * s.L, s.tokens)
         Lc = ee - ss
         cache.kvcache_compression = True
-        cache.keypatches_mask_chunk = mask[ss:ee]
+        cache.keypatches_mask_chunk = mask[ss:ee]            # (LLaVA: only the first t*196 of the t*729 entries land on tokens)
         for layer in range(s.layers):
             j = it % pool
             it += 1
-            pos = pos_grid[:, :, :Lc].clone()
+            pos = pos_grid[..., :Lc].clone()
             if s.reforge:
                 pos[0] += cache.get_prev_temporal_idx(layer) + 1
             else:
-                pos[0] += c * (s.L // s.N)
+                pos[0] += c * (s.L // s.tok_per_grid if s.mrope else s.L)
             if timer is not None:
                 timer.arm(cache)
             cache.update(k[j:j + 1, :Lc].transpose(1, 2), v[j:j + 1, :Lc].transpose(1, 2), layer,
@@ -222,8 +241,11 @@ def cpu_reference_step(s, sample_T, host, it):
     out, mask, _ = ro.dpselect(x[None, :sample_T], tt, False)
     t1 = time.perf_counter()
     j = it % q.shape[0]
-    rot = TableRotary(s.D)
-    pos = torch.stack([torch.arange(s.L) // s.N, (torch.arange(s.L) % s.N) // 16, torch.arange(s.L) % 16])[:, None]
+    rot = TableRotary(s.D, mrope=s.mrope is not None)
+    if s.mrope:
+        pos = torch.stack([torch.arange(s.L) // s.N, (torch.arange(s.L) % s.N) // 16, torch.arange(s.L) % 16])[:, None]
+    else:
+        pos = torch.arange(s.L)[None]
     ro.pivot_update(q[j:j + 1].transpose(1, 2), k[j:j + 1].transpose(1, 2), v[j:j + 1].transpose(1, 2), s.kv_ratio,
                     mask[:s.L] if mask.numel() >= s.L else None, pos, rot, s.mrope, s.reforge)
     t2 = time.perf_counter()
@@ -236,12 +258,13 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     s = Shape(a)
-    workload = (f"Qwen2-VL-7B-shape {s.frames} frames @448px: DPSelect X[1,{s.T},{s.N},{s.C}] r_v={s.t / s.T:.3g} "
+    model = "Qwen2-VL-7B-shape" if s.name == "qwen2vl" else "LLaVA-Video-Qwen2-7B-shape (SigLIP-so400m grid)"
+    workload = (f"{model} {s.frames} frames @448px: DPSelect X[1,{s.T},{s.N},{s.C}] r_v={s.t / s.T:.3g} "
                 f"patch_sync=False + PivotKV {s.chunks} chunks x {s.layers} layers, L={s.L}, H={s.H}, KVH={s.KVH}, "
                 f"D={s.D}, r_kv={s.kv_ratio:.4g} (keep {s.keep}), reforge={s.reforge}")
     config = {"workload": workload, "frames": s.frames, "visual_ratio": s.t / s.T, "kv_ratio": s.kv_ratio,
               "pos_embed_reforge": s.reforge, "qkv_pool": a.pool,
-              "l2_policy": "inputs larger than L2 (X 1.9 GB; Q/K/V pool cycled, reuse distance > 126 MB)",
+              "l2_policy": f"inputs larger than L2 (X {2 * s.T * s.N * s.C / 1e9:.2f} GB; Q/K/V pool cycled, reuse distance > 126 MB)",
               "parallelism": f"dp{world} (one video per GPU, no data-path collective)"}
 
     if a.impl == "reference":
@@ -279,11 +302,11 @@ def main():
     from retake import longvideo_cache as lc
     from retake import visual_compression as vc
     timer = ScoreTimer()
-    rotary = make_rotary(dev)
+    rotary = make_rotary(dev, s.name)
     host = synth_host(s, a.pool, 1234 + rank)
     x, q, k, v = [h.to(dev, non_blocking=True) for h in host]
     ar = torch.arange(s.L, device=dev)
-    pos_grid = torch.stack([ar // s.N, (ar % s.N) // 16, ar % 16])[:, None]
+    pos_grid = torch.stack([ar // s.N, (ar % s.N) // 16, ar % 16])[:, None] if s.mrope else ar[None]
     torch.cuda.synchronize()
 
     def sync_all():

@@ -1,0 +1,39 @@
+"""GPU probe: touch every kernel once at small, ragged sizes (run under compute-sanitizer memcheck / racecheck)."""
+import os, sys, types
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+for p in (ROOT, os.path.join(ROOT, "video-retake_b200"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import torch
+from helpers import TableRotary, scene_video
+from retake import longvideo_cache as lc
+from retake import visual_compression as vc
+
+g = torch.Generator().manual_seed(0)
+for (T, N, C) in ((9, 5, 256), (7, 33, 1152), (5, 3, 3584)):
+    x = scene_video(g, T, N, C, dup_every=3).to(torch.bfloat16).cuda()
+    for sync in (False, True):
+        for t in (T, max(1, T // 2), 1):
+            out, mask, idx = vc.memory_bank_compress_keyframe(x[None], t, 3, sync=sync, return_indices=True)
+    d = vc.dpselect_distance(x[1:], halo=True)
+for (H, KVH, L, D) in ((4, 2, 130, 64), (28, 4, 200, 128), (8, 8, 1, 128)):
+    cfg = types.SimpleNamespace(hidden_size=H * D, num_hidden_layers=2, num_attention_heads=H, num_key_value_heads=KVH)
+    for reforge in (False, True):
+        cfg.longvideo_kwargs = {"kvcache_compression": True, "kvcache_compression_kwargs": {
+            "compression_ratio": 0.3, "compression_method": "pivotkv", "pos_embed_reforge": reforge}}
+        cache = lc.PivotKVCache(cfg)
+        rot = TableRotary(D)
+        rot.inv_freq = rot.inv_freq.cuda()
+        sec = [D // 8, 3 * D // 16, 3 * D // 16]
+        for chunk in range(2):
+            for layer in range(2):
+                q = torch.randn(1, L, H, D, generator=g).to(torch.bfloat16).cuda().transpose(1, 2)
+                k = torch.randn(1, L, KVH, D, generator=g).to(torch.bfloat16).cuda().transpose(1, 2)
+                v = torch.randn(1, L, KVH, D, generator=g).to(torch.bfloat16).cuda().transpose(1, 2)
+                ar = torch.arange(L, device="cuda")
+                pos = torch.stack([chunk * 10 + ar // 16, (ar % 16) // 4, ar % 4])[:, None]
+                cache.keypatches_mask_chunk = (torch.rand(L, generator=g) < 0.3).cuda()
+                cache.update(k, v, layer, {"query_states": q, "position_ids": pos, "rotary_emb": rot, "mrope_section": sec})
+        cache.after_forward()
+        _ = cache.layers[0].keys.sum().item()
+torch.cuda.synchronize()
+print("sanitize pass done")
