@@ -342,14 +342,33 @@ def main():
     e2e = None
     if not a.no_e2e:
         h2d = sum(h.numel() * h.element_size() for h in host)
-        xd, qd, kd, vd = [torch.empty_like(h, device=dev) for h in host]
+        # two device input sets: the H2D copy of step i+1 runs on a copy stream while step i computes (a serving loop
+        # would do the same); every step still copies all of its inputs from pinned host memory and reads its result back
+        bufs = [[torch.empty_like(h, device=dev) for h in host] for _ in range(2)]
+        copy_stream = torch.cuda.Stream(device=dev)
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        freed = [torch.cuda.Event(), torch.cuda.Event()]
+
+        def enqueue_copy(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(freed[i % 2])
+                for dst, src in zip(bufs[i % 2], host):
+                    dst.copy_(src, non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
         sync_all()
+        for ev in freed:
+            ev.record()
         e0.record()
         d2h = 0
-        for _ in range(a.steps):
-            for dst, src in zip((xd, qd, kd, vd), host):
-                dst.copy_(src, non_blocking=True)
+        enqueue_copy(0)
+        for i in range(a.steps):
+            if i + 1 < a.steps:
+                enqueue_copy(i + 1)
+            torch.cuda.current_stream().wait_event(ready[i % 2])
+            xd, qd, kd, vd = bufs[i % 2]
             keep_idx, seq = run_step(s, xd, qd, kd, vd, rotary, lc, vc, pos_grid)
+            freed[i % 2].record()
             back = keep_idx.cpu()
             d2h = back.numel() * back.element_size()
         e1.record()
@@ -361,7 +380,7 @@ def main():
             ems = float(t)
         e2e = {"value": world * s.frames / (ems / a.steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h}
-        del xd, qd, kd, vd
+        del bufs
 
     if rank != 0:
         if dist is not None:

@@ -119,24 +119,26 @@ pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
 constexpr int kSelThreads = 1024;
 
 // block-wide: ascending indices of the `keep` largest radix keys in keys[0..L); ties -> lowest index.
-__device__ void block_select_top(const uint32_t* keys, int L, int keep, int32_t* out_idx, int* sh /* >= 72 ints */,
+__device__ void block_select_top(const uint32_t* keys, int L, int keep, int32_t* out_idx, int* sh /* >= 104 ints */,
                                  int low_bit /* keys are multiples of 2^low_bit */) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (L + kSelThreads - 1) / kSelThreads;
     const int beg = min(tid * per, L), end = min(beg + per, L);
-    // bitwise descent for the keep-th largest key: one counter per bit (zeroed up front), one barrier per bit
-    if (tid < 32) sh[40 + tid] = 0;
-    __syncthreads();
+    // bitwise descent for the keep-th largest key: per-warp counts -> shared -> every warp folds the 32 counts itself
+    // (two barriers per bit, no serialised atomics; the two count buffers alternate so no third barrier is needed)
     uint32_t prefix = 0;
     for (int bit = 31; bit >= low_bit; --bit) {
         const uint32_t cand = prefix | (1u << bit);
         int cnt = 0;
         for (int i = beg; i < end; ++i) cnt += (keys[i] >= cand);
         cnt = __reduce_add_sync(0xffffffffu, cnt);
-        if (lane == 0 && cnt) atomicAdd(&sh[40 + bit], cnt);
+        int* buf = sh + 40 + 32 * (bit & 1);
+        if (lane == 0) buf[warp] = cnt;
         __syncthreads();
-        if (sh[40 + bit] >= keep) prefix = cand;
+        const int total = __reduce_add_sync(0xffffffffu, buf[lane]);
+        if (total >= keep) prefix = cand;
     }
+    __syncthreads();
     // skipped low bits: the radix transform sets them to ones for negative values (and for NaN), to zeros otherwise
     if (low_bit > 0 && (!(prefix & 0x80000000u) || (prefix >> low_bit) == (0xffffffffu >> low_bit)))
         prefix |= (1u << low_bit) - 1u;
@@ -341,7 +343,7 @@ extern "C" int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L,
                                 int32_t* keep_idx, void* score_out, void* stream) {
     if (!head_scores || !keep_idx || KVH < 1 || L < 1 || keep < 1 || keep > L) return RTK_E_BADARG;
     if (L > 16384) return RTK_E_UNSUPPORTED;
-    const size_t smem = (size_t)L * 4 + 80 * 4;
+    const size_t smem = (size_t)L * 4 + 112 * 4;
     cudaError_t e = cudaFuncSetAttribute(pivot_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     pivot_select_kernel<<<1, kSelThreads, smem, (cudaStream_t)stream>>>(
