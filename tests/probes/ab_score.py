@@ -10,6 +10,7 @@ hs = torch.empty(KVH, L, dtype=torch.bfloat16, device="cuda")
 ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
 libs = sorted(glob.glob(os.path.join(ROOT, "build", "ab", "librtk_*.so")))
 res = {}
+outs = {}
 p, i64, sz = C.c_void_p, C.c_int64, C.c_size_t
 for rnd in range(3):
     for path in libs:
@@ -22,6 +23,7 @@ for rnd in range(3):
         for _ in range(5):
             assert call() == 0
         torch.cuda.synchronize()
+        outs[os.path.basename(path)] = hs.clone()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(50):
@@ -30,3 +32,5 @@ for rnd in range(3):
         torch.cuda.synchronize()
         res.setdefault(os.path.basename(path), []).append(a.elapsed_time(b) / 50)
 print(json.dumps(res, indent=1))
+ref = outs[sorted(outs)[0]]
+print({n: int((o.view(torch.int16) != ref.view(torch.int16)).sum()) for n, o in outs.items()}, 'mismatches vs first variant')

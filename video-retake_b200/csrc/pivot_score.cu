@@ -20,6 +20,9 @@
 #ifndef RTK_SCORE_EXPERIMENT_NOMATH
 #define RTK_SCORE_EXPERIMENT_NOMATH 0
 #endif
+#ifndef RTK_SCORE_EXPERIMENT_NOLOAD
+#define RTK_SCORE_EXPERIMENT_NOLOAD 0
+#endif
 #ifndef RTK_SCORE_EXPERIMENT_NOEXP
 #define RTK_SCORE_EXPERIMENT_NOEXP 0
 #endif
@@ -40,9 +43,9 @@ struct ScoreSmem {
     static constexpr uint32_t b_ring = kTileBytes;
     static constexpr uint32_t stats = b_ring + kStages * kTileBytes;                 // [kStatSlots][128] f32
     static constexpr uint32_t merge = stats + kStatSlots * kTile * 4;                // [4][128][2] f32
-    static constexpr uint32_t bars = merge + 4 * kTile * 2 * 4;
-    // barriers: a_full, a_empty, b_full[4], b_empty[4], t_full[4], t_empty[4], st_full[8]
-    static constexpr uint32_t n_bars = 2 + 2 * kStages + 2 * kAccBufs + kStatSlots;
+    static constexpr uint32_t bars = merge + 8 * kTile * 2 * 4;          // up to 8 groups
+    // barriers: a_full, a_empty, b_full[4], b_empty[4], t_full[4], t_empty[4], st_full[8], port
+    static constexpr uint32_t n_bars = 2 + 2 * kStages + 2 * kAccBufs + kStatSlots + 1;
     static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
     static constexpr uint32_t total = tmem_ptr + 16;
 };
@@ -194,8 +197,23 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 // bf16x2 -> (lo, hi) widened to fp32, packed for the x2 pipes
 __device__ __forceinline__ uint64_t widen2(uint32_t p) { return pk2(bf16lo_to_f32(p), bf16hi_to_f32(p)); }
 
+#ifndef RTK_SCORE_RZPACK
+#define RTK_SCORE_RZPACK 1     // round to bf16 in place (F2FP with a zero low half: the result IS the fp32 value; default, -5 %) vs pack + widen (0)
+#endif
+// fp32 -> nearest bf16, returned as fp32: one F2FP.BF16.F32.PACK_AB whose low half is RZ
+__device__ __forceinline__ float round_bf16_inplace(float a) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(0.f));
+    return __uint_as_float(d);
+}
+
 // the reference's logit rounding chain on a pair of raw accumulators: bf16(acc) then bf16(x * inv_sqrt_d); fp32 out
 __device__ __forceinline__ uint64_t logit_chain2(uint32_t r0, uint32_t r1, uint64_t inv2) {
+#if RTK_SCORE_RZPACK
+    float t0, t1;
+    upk2(mul2(pk2(round_bf16_inplace(__uint_as_float(r0)), round_bf16_inplace(__uint_as_float(r1))), inv2), t0, t1);
+    return pk2(round_bf16_inplace(t0), round_bf16_inplace(t1));
+#endif
     const uint32_t p1 = pack_bf16x2_rn(__uint_as_float(r0), __uint_as_float(r1));
     float s0, s1;
     upk2(mul2(widen2(p1), inv2), s0, s1);
@@ -208,6 +226,9 @@ __device__ __forceinline__ float logit_chain1(float acc, float inv) { return rou
 #endif
 #ifndef RTK_SCORE_X64
 #define RTK_SCORE_X64 1          // one 64-column TMEM load per tile half (default; -2 % vs two 32-column loads)
+#endif
+#ifndef RTK_SCORE_PORT
+#define RTK_SCORE_PORT 0
 #endif
 #ifndef RTK_SCORE_X32DB
 #define RTK_SCORE_X32DB 0
@@ -346,8 +367,13 @@ struct TileRange {
     }
 };
 
-constexpr int kSoftmaxWarps = 16;     // four groups of four warps (one per TMEM lane quarter)
+#ifndef RTK_SCORE_GROUPS
+#define RTK_SCORE_GROUPS 0     // 0: four groups, tiles alternate between two group pairs (64 columns per group);
+#endif                         // G > 0: G groups take the 32-column chunks of all tiles round robin
+constexpr int kGroups = RTK_SCORE_GROUPS ? RTK_SCORE_GROUPS : 4;
+constexpr int kSoftmaxWarps = 4 * kGroups;     // groups of four warps (one per TMEM lane quarter)
 constexpr int kScoreThreads2 = (2 + kSoftmaxWarps) * 32;
+constexpr int kTileArrivals = RTK_SCORE_GROUPS ? 16 : 8;       // softmax-warp arrivals that free one accumulator buffer
 
 template <int PASS>
 __global__ void __launch_bounds__(kScoreThreads2, 1)
@@ -365,13 +391,15 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
     auto t_full = [&](int b) { return bar0 + 16 + 8 * (2 * kStages + b); };
     auto t_empty = [&](int b) { return bar0 + 16 + 8 * (2 * kStages + kAccBufs + b); };
     auto st_full = [&](int i) { return bar0 + 16 + 8 * (2 * kStages + 2 * kAccBufs + i); };
+    const uint32_t port = bar0 + 16 + 8 * (2 * kStages + 2 * kAccBufs + kStatSlots);
 
     if (threadIdx.x == 0) {
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
         for (int s = 0; s < kStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
-        for (int b = 0; b < kAccBufs; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), 8); }
+        for (int b = 0; b < kAccBufs; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), kTileArrivals); }
         for (int i = 0; i < kStatSlots; ++i) mbar_init(st_full(i), 1);
+        mbar_init(port, 8);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(base + ScoreSmem::tmem_ptr, 512);
@@ -469,6 +497,31 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
         while (range.next(u, tb0, tb1)) {
             const int h = u / nt, ta = u - h * nt;
             SoftmaxState st;
+#if RTK_SCORE_GROUPS
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                const int b = cnt % kAccBufs;
+                bool waited = false;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if ((int)((cnt * 4u + c) % kGroups) != grp) continue;
+                    if (!waited) {
+                        mbar_wait(t_full(b), (cnt / kAccBufs) & 1u);
+                        tc_fence_after();
+                        if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
+                        waited = true;
+                    }
+                    const int valid_c = prm.L - tb * kTile - c * 32;
+                    const float* cqc = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + c * 32;
+                    uint32_t r[32];
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + b * kTile + c * 32, r);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 32>(r, 0, valid_c, st, cqc, inv, inv2, l2e2);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty(b));
+                }
+            }
+#else
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 if ((int)(cnt & 1u) != (grp >> 1)) continue;
                 const int b = cnt % kAccBufs;
@@ -494,8 +547,21 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
 #elif RTK_SCORE_X64
                 {
                     uint32_t r[64];
+#if RTK_SCORE_PORT
+                    // TMEM read port token: the eight warps of tile n read their 64 KiB only after those of tile n-1 have
+                    // theirs, so one group pair computes while the other one loads instead of both contending for the port
+                    if (cnt > 0) mbar_wait(port, (cnt - 1) & 1u);
+#endif
+#if RTK_SCORE_EXPERIMENT_NOLOAD             // timing experiment: all the arithmetic on made-up accumulators, no TMEM read
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) r[i] = 0x3f000000u + (uint32_t)(row + tb) * 0x1000u + (uint32_t)i * 0x20000u;
+#else
                     tmem_ld64(taddr, r);
                     tmem_ld_wait();
+#endif
+#if RTK_SCORE_PORT
+                    if (lane == 0) mbar_arrive(port);
+#endif
                     softmax_cols<PASS, 64>(r, 0, valid, st, cq, inv, inv2, l2e2);
                 }
 #elif RTK_SCORE_X32DB
@@ -520,6 +586,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty(b));
             }
+#endif
             const float m = st.m;
             // ---- fold the four groups and write this CTA's share of the unit
             float a0, a1;
@@ -531,30 +598,32 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
             if (PASS == 1) {
                 merge[(grp * kTile + row) * 2] = m;
                 merge[(grp * kTile + row) * 2 + 1] = a0 + a1;
-                asm volatile("bar.sync 1, 512;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
                 if (grp == 0) {
                     float mn = -INFINITY;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) mn = fmaxf(mn, merge[(g * kTile + row) * 2]);
+                    for (int g = 0; g < kGroups; ++g) mn = fmaxf(mn, merge[(g * kTile + row) * 2]);
                     float lt = 0.f;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {
+                    for (int g = 0; g < kGroups; ++g) {
                         const float mg = merge[(g * kTile + row) * 2];
                         if (mg > -INFINITY) lt += merge[(g * kTile + row) * 2 + 1] * ex2f((mg - mn) * kLog2e);
                     }
                     prm.ml_part[(size_t)part * hl + o] = make_float2(mn, lt);
                     if (whole) prm.ml_part[hl + o] = make_float2(-INFINITY, 0.f);
                 }
-                asm volatile("bar.sync 1, 512;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
             } else {
                 merge[grp * kTile + row] = a0 + a1;
-                asm volatile("bar.sync 1, 512;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
                 if (grp == 0) {
-                    prm.colsum_part[(size_t)part * hl + o] =
-                        ((merge[row] + merge[kTile + row]) + merge[2 * kTile + row]) + merge[3 * kTile + row];
+                    float cs = merge[row];
+#pragma unroll
+                    for (int g = 1; g < kGroups; ++g) cs += merge[g * kTile + row];
+                    prm.colsum_part[(size_t)part * hl + o] = cs;
                     if (whole) prm.colsum_part[hl + o] = 0.f;
                 }
-                asm volatile("bar.sync 1, 512;" ::: "memory");
+                asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
             }
         }
     }
