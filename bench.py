@@ -404,7 +404,8 @@ def main():
                 # dram__bytes_read.sum + dram__bytes_write.sum of both launches, profiles/r1_ncu_score_summary.txt (L=4096)
                 "traffic": 67.6e6 if s.L == 4096 else None,
                 "note": ("algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it twice and is bounded by the "
-                         "TMEM read port, not the tensor pipe (DESIGN.md section 5)")}
+                         "softmax warps' instruction stream (math-only 0.349 ms, TMEM-only floor 0.238 ms), not the tensor pipe "
+                         "(DESIGN.md section 5)")}
     dps_ms = sum(a.elapsed_time(b) for a, b in timer.dpselect) / max(1, len(timer.dpselect))
     hbm = peaks.get("hbm_gbs", 6650.0)
     dps_bytes = 2.0 * s.T * s.N * s.C + 4.0 * s.T * s.N + 4.0 * s.t * s.N * s.C

@@ -373,7 +373,11 @@ struct TileRange {
 constexpr int kGroups = RTK_SCORE_GROUPS ? RTK_SCORE_GROUPS : 4;
 constexpr int kSoftmaxWarps = 4 * kGroups;     // groups of four warps (one per TMEM lane quarter)
 constexpr int kScoreThreads2 = (2 + kSoftmaxWarps) * 32;
-constexpr int kTileArrivals = RTK_SCORE_GROUPS ? 16 : 8;       // softmax-warp arrivals that free one accumulator buffer
+#ifndef RTK_SCORE_GCOLS
+#define RTK_SCORE_GCOLS 32     // chunk width of the round-robin scheme
+#endif
+constexpr int kChunksPerTile = 128 / RTK_SCORE_GCOLS;
+constexpr int kTileArrivals = RTK_SCORE_GROUPS ? 4 * kChunksPerTile : 8;       // softmax-warp arrivals that free one accumulator buffer
 
 template <int PASS>
 __global__ void __launch_bounds__(kScoreThreads2, 1)
@@ -502,20 +506,24 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 const int b = cnt % kAccBufs;
                 bool waited = false;
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if ((int)((cnt * 4u + c) % kGroups) != grp) continue;
+                for (int c = 0; c < kChunksPerTile; ++c) {
+                    if ((int)((cnt * (unsigned)kChunksPerTile + c) % kGroups) != grp) continue;
                     if (!waited) {
                         mbar_wait(t_full(b), (cnt / kAccBufs) & 1u);
                         tc_fence_after();
                         if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
                         waited = true;
                     }
-                    const int valid_c = prm.L - tb * kTile - c * 32;
-                    const float* cqc = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + c * 32;
-                    uint32_t r[32];
+                    const int valid_c = prm.L - tb * kTile - c * RTK_SCORE_GCOLS;
+                    const float* cqc = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + c * RTK_SCORE_GCOLS;
+                    uint32_t r[RTK_SCORE_GCOLS];
+#if RTK_SCORE_GCOLS == 64
+                    tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + b * kTile + c * 64, r);
+#else
                     tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + b * kTile + c * 32, r);
+#endif
                     tmem_ld_wait();
-                    softmax_cols<PASS, 32>(r, 0, valid_c, st, cqc, inv, inv2, l2e2);
+                    softmax_cols<PASS, RTK_SCORE_GCOLS>(r, 0, valid_c, st, cqc, inv, inv2, l2e2);
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty(b));
