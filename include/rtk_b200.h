@@ -75,6 +75,22 @@ int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t C, const in
  * to a frame range).  src_row is int64 [rows] on the device. */
 int rtk_gather_rows(const void* x, int64_t row_bytes, const int64_t* src_row, int64_t rows, void* out, void* stream);
 
+/* MA-LLM compressors: the caller's loop `while T > t: bank(, size) = memory_bank_compress_MALLM[_hard](...)`
+ * (retake/qwen2_vl.py:402-409, retake/llava_onevision.py:235-243 around visual_compression.py:5-47 / :50-83) in one call.
+ *   x         bf16 [T, N, C] (not modified);  sizes_in bf16 [T, N] or NULL (= ones): frames each row stands for
+ *   t         frames to keep, 1 <= t <= T (t = T - 1 is exactly one call of the reference function)
+ *   sync      0: every patch column merges its own most similar adjacent pair;  1: one pair for all patches, chosen on
+ *             the bf16 mean of the similarities over the patches (visual_compression.py:21-22)
+ *   hard      0: size-weighted average of the pair (:38-46);  1: the first frame of the pair is dropped (:73-79)
+ *   out       bf16 [t, N, C];  sizes_out bf16 [t, N] (ignored when hard)
+ *   workspace >= rtk_mallm_workspace_bytes(T, N, C, hard) bytes, 256-byte aligned; holds the per-(frame, patch) state
+ *             and, for the soft variant, one rewritable copy of the bank.
+ * Results are bit-identical to the reference's torch-CUDA op sequence for bf16 banks (every intermediate rounded to
+ * bf16, sizes counted in bf16, lowest index among equal similarities). */
+size_t rtk_mallm_workspace_bytes(int64_t T, int64_t N, int64_t C, int hard);
+int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T, int64_t N, int64_t C, int64_t t, int sync, int hard,
+                       void* out, void* sizes_out, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * PivotKV  (retake/longvideo_cache.py)
  * ---------------------------------------------------------------------------------------------------- */

@@ -68,8 +68,9 @@ def aten_cuda_rowsum(xf: torch.Tensor, vec: int = 8, square: bool = False) -> to
     return lane[:, 0]
 
 
-def adjacent_cosine_distance(x: torch.Tensor, reduce: str = "torch", norm_vec: int = 4, sum_vec: int = 8) -> torch.Tensor:
-    """``dis[T, N]`` fp32 for a memory bank ``x[T, N, C]`` (``visual_compression.py:98-106``).
+def adjacent_cosine_similarity(x: torch.Tensor, reduce: str = "torch", norm_vec: int = 4, sum_vec: int = 8) -> torch.Tensor:
+    """``sim[T-1, N]`` (fp32 container; bf16-valued for a bf16 bank) between consecutive frames of ``x[T, N, C]``:
+    the rounding chain of ``F.cosine_similarity`` (``visual_compression.py:20,63,100``).
 
     ``reduce="aten_cuda"``: ``linalg_vector_norm`` on bf16 reduces with 4-element vectors, ``sum`` on bf16
     with 8-element vectors (measured on the B200, tests/probes/probe_aten_cuda2.py Q6/Q7)."""
@@ -89,8 +90,13 @@ def adjacent_cosine_distance(x: torch.Tensor, reduce: str = "torch", norm_vec: i
     n = torch.maximum(n, eps)
     u = rnd(xf / n[..., None])
     p = rnd(u[:-1] * u[1:])
-    sim = rnd(rowsum(p))
-    dis = 1.0 - sim
+    return rnd(rowsum(p))
+
+
+def adjacent_cosine_distance(x: torch.Tensor, reduce: str = "torch", norm_vec: int = 4, sum_vec: int = 8) -> torch.Tensor:
+    """``dis[T, N]`` fp32 for a memory bank ``x[T, N, C]`` (``visual_compression.py:98-106``): one minus the adjacent
+    similarity, row 0 = 1."""
+    dis = 1.0 - adjacent_cosine_similarity(x, reduce, norm_vec, sum_vec)
     return torch.cat([torch.ones_like(dis[:1]), dis], dim=0)
 
 

@@ -73,3 +73,50 @@ def pivot_update(q, k, v, ratio, keymask=None, position_ids=None, rotary=None, s
         c, s = _mrope_pick(cos, sections), _mrope_pick(sin, sections)
         kk = (kk * c) + (_half_turn(kk) * s)
     return kk, vv, pos, idx, score
+
+
+def _closest_pair(bank, sync):
+    """index [1, 1, N] of the most similar adjacent frame pair (``visual_compression.py:20-24``)"""
+    cos = F.cosine_similarity(bank[:, :-1], bank[:, 1:], dim=-1)
+    if sync:
+        cos = cos.mean(-1, keepdim=True).expand(-1, -1, bank.shape[2])
+    return torch.max(cos, dim=1, keepdim=True)[1]
+
+
+def mallm_round(bank, size, sync=False):
+    """one MA-LLM merge with stock torch ops: ``[1, T, N, C]``, ``[1, T, N]`` -> ``[1, T-1, N, C]``, ``[1, T-1, N]``"""
+    _, T, N, C = bank.shape
+    first = _closest_pair(bank, sync)
+    rest = torch.arange(T - 1, device=bank.device)[None, :, None].repeat(1, 1, N)
+    rest = rest + (rest > first).long()                                   # every frame but first + 1
+    wide = lambda i: i.unsqueeze(-1).expand(-1, -1, -1, C)
+    moved, moved_n = bank.gather(1, wide(first + 1)), size.gather(1, first + 1)
+    kept, kept_n = bank.gather(1, wide(rest)), size.gather(1, rest)
+    moved *= moved_n.unsqueeze(-1)
+    kept *= kept_n.unsqueeze(-1)
+    kept.scatter_add_(1, wide(first), moved)
+    kept_n.scatter_add_(1, first, moved_n)
+    return kept / kept_n.unsqueeze(-1), kept_n
+
+
+def mallm_hard_round(bank, sync=False):
+    """one MA-LLM-hard step: the first frame of the closest pair is overwritten by the second"""
+    _, T, N, C = bank.shape
+    first = _closest_pair(bank, sync)
+    rest = torch.arange(T - 1, device=bank.device)[None, :, None].repeat(1, 1, N)
+    rest = rest + (rest > first).long()
+    wide = lambda i: i.unsqueeze(-1).expand(-1, -1, -1, C)
+    kept = bank.gather(1, wide(rest))
+    kept.scatter_(1, wide(first), bank.gather(1, wide(first + 1)))
+    return kept
+
+
+def mallm_compress(bank, t, sync=False, hard=False):
+    """the caller's loop (``qwen2_vl.py:402-409``)"""
+    size = torch.ones_like(bank[:, :, :, 0])
+    while bank.shape[1] > t:
+        if hard:
+            bank = mallm_hard_round(bank, sync)
+        else:
+            bank, size = mallm_round(bank, size, sync)
+    return (bank, None) if hard else (bank, size)

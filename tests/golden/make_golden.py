@@ -12,7 +12,7 @@ It imports ``retake.visual_compression.memory_bank_compress_keyframe`` and
 ``layers[i].keys`` instead, so the reference class is instantiated through a subclass that
 only adds ``key_cache`` / ``value_cache`` list views - the reference code is not edited.
 
-Outputs: ``tests/golden/dpselect_*.pt`` and ``tests/golden/pivotkv_*.pt`` (inputs + outputs,
+Outputs: ``tests/golden/dpselect_*.pt``, ``tests/golden/pivotkv_*.pt`` and ``tests/golden/mallm_*.pt`` (inputs + outputs,
 bf16 stored as such; a few hundred KB in total).
 """
 import os
@@ -180,8 +180,37 @@ def gen_pivotkv(lc):
     print("pivotkv cases:", len(out))
 
 
+def gen_mallm(vc):
+    """the caller's loop around memory_bank_compress_MALLM / _MALLM_hard (qwen2_vl.py:402-409), every round frozen"""
+    g = torch.Generator().manual_seed(4321)
+    out = []
+    for name, T, N, C, dt, dup, t in [("mallm_f32", 14, 6, 32, torch.float32, 0, 5),
+                                      ("mallm_bf16", 16, 9, 64, torch.bfloat16, 0, 6),
+                                      ("mallm_dup_bf16", 20, 10, 128, torch.bfloat16, 4, 3),
+                                      ("mallm_bf16_wide", 10, 136, 32, torch.bfloat16, 3, 4)]:
+        X = scene_video(g, T, N, C, dup_every=dup)[None].to(dt)
+        for sync in (False, True):
+            bank, size = X.clone(), torch.ones_like(X[:, :, :, 0])
+            hard = X.clone()
+            rounds = []
+            while bank.shape[1] > t:
+                bank, size = vc.memory_bank_compress_MALLM(bank, size, sync=sync)
+                hard = vc.memory_bank_compress_MALLM_hard(hard, sync=sync)
+                rounds.append({"bank": bank.clone(), "size": size.clone(), "hard": hard.clone()})
+            keep = [0, len(rounds) // 2, len(rounds) - 1]                # first / middle / last round only (file size)
+            out.append({"name": name, "x": X, "t": t, "sync": sync, "n_rounds": len(rounds),
+                        "rounds": {i: rounds[i] for i in keep}})
+    torch.save(out, os.path.join(HERE, "mallm_reference.pt"))
+    print("mallm cases:", len(out))
+
+
 if __name__ == "__main__":
     torch.set_num_threads(4)
     vc, lc = load_reference()
-    gen_dpselect(vc)
-    gen_pivotkv(lc)
+    which = sys.argv[1:] or ["dpselect", "pivotkv", "mallm"]
+    if "dpselect" in which:
+        gen_dpselect(vc)
+    if "pivotkv" in which:
+        gen_pivotkv(lc)
+    if "mallm" in which:
+        gen_mallm(vc)

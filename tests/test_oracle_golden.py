@@ -202,3 +202,57 @@ def test_reference_ops_pivot_update_bit_identical(case):
             assert torch.equal(pos, st["position_cache"])
         n += 1
     assert n >= 1
+
+
+# ------------------------------------------------------------------------------------------- MA-LLM compressors
+from oracle import mallm as om  # noqa: E402
+
+ML = torch.load(os.path.join(G, "mallm_reference.pt"))
+
+
+def _replay_mallm(case, soft_round, hard_round):
+    bank, size = case["x"].clone(), torch.ones_like(case["x"][:, :, :, 0])
+    hard = case["x"].clone()
+    for r in range(case["n_rounds"]):
+        bank, size = soft_round(bank, size, case["sync"])
+        hard = hard_round(hard, case["sync"])
+        if r in case["rounds"]:
+            want = case["rounds"][r]
+            assert torch.equal(bank, want["bank"]) and torch.equal(size, want["size"]), f"soft round {r}"
+            assert torch.equal(hard, want["hard"]), f"hard round {r}"
+    assert bank.shape[1] == case["t"]
+
+
+@pytest.mark.parametrize("case", ML, ids=lambda c: f"{c['name']}-{'sync' if c['sync'] else 'patch'}")
+def test_mallm_explicit_oracle_matches_reference_every_round(case):
+    def soft(b, s, sync):
+        o, z, _ = om.mallm_round(b[0], s[0], sync)
+        return o[None], z[None]
+    _replay_mallm(case, soft, lambda b, sync: om.mallm_hard_round(b[0], sync)[0][None])
+
+
+@pytest.mark.parametrize("case", ML, ids=lambda c: f"{c['name']}-{'sync' if c['sync'] else 'patch'}")
+def test_mallm_reference_ops_match_reference_every_round(case):
+    _replay_mallm(case, ro.mallm_round, ro.mallm_hard_round)
+
+
+def test_mallm_rescale_map_is_idempotent():
+    """x -> rd(rd(x * s) / s) reaches a fixed point after ONE application for every bf16 mantissa and every size the
+    kernels can meet - the property the incremental CUDA implementation leans on (it still re-checks dynamically)."""
+    m = torch.arange(128, dtype=torch.float32) / 128 + 1
+    x = torch.cat([m * 2.0 ** e for e in (-3, 0, 2)]).to(torch.bfloat16)
+    for s in range(1, 1025):
+        sb = torch.tensor(float(s)).to(torch.bfloat16)
+        if float(sb) != s:
+            continue
+        once = (x * sb) / sb
+        assert torch.equal((once * sb) / sb, once)
+
+
+def test_aten_cuda_rowmean_model_is_a_mean():
+    g = torch.Generator().manual_seed(2)
+    for n in (24, 96, 128, 136, 256, 729):
+        v = torch.randn(11, n, generator=g).to(torch.bfloat16).float()
+        got = om.aten_cuda_bf16_rowmean(v)
+        want = v.double().mean(-1).float()
+        assert torch.allclose(got, want, rtol=2 ** -7, atol=1e-3)

@@ -8,7 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "librtk_b200.so")
-SOURCES = ["dpselect.cu", "pivot_score.cu", "pivot_misc.cu"]
+SOURCES = ["dpselect.cu", "mallm.cu", "pivot_score.cu", "pivot_misc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v", "-DNDEBUG"]

@@ -1,0 +1,527 @@
+// MA-LLM memory-bank compressors (sm_100a): the `compression_method: MA-LLM / MA-LLM-hard` branch of
+// compress_video_tokens (retake/qwen2_vl.py:402-409, retake/llava_onevision.py:235-243), i.e. the loop
+//     while T > tgt: bank, size = memory_bank_compress_MALLM(bank, size, sync)      (visual_compression.py:5-47)
+//     while T > tgt: bank = memory_bank_compress_MALLM_hard(bank, sync)             (visual_compression.py:50-83)
+// fused into one call.  The reference recomputes every cosine similarity and rewrites the whole bank on every
+// round (O(rounds * T*N*C) bytes); here the bank is read once and each round only touches what changed:
+//
+//   * state per (frame i, patch p): similarity to the next surviving frame, norm, size, next/prev links, flags;
+//   * a round = argmax over the similarities (lowest index among equals, NaN first - torch.max on CUDA), the merge
+//     of frames m and next(m), and the replay of the reference's `x = rd(rd(x * size) / size)` on the rows for
+//     which that map is not yet at a fixed point (it is idempotent after one or two applications, so the "dirty"
+//     list holds the rows changed in the previous round only), then the similarities next to changed rows;
+//   * sync mode shares one argmax over the bf16 mean of the similarities across patches (second kernel per round).
+//
+// Arithmetic is the reference's, bit for bit (bf16 bank): rd() = round to nearest even to bf16 after EVERY op,
+// true fp32 division, sizes kept in bf16; cosine similarity as in dpselect.cu (ATen reduction orders: 4-element
+// vectors for the norm, 8-element vectors for the product sum); the sync mean replays ATen's bf16 mean(-1)
+// (8-element vectors, block width min(last_pow2(N/8), 32), unaligned head / tail by the row's position in the
+// CURRENT bank - which is why all means are refreshed every round when N % 8 != 0).
+#include <math.h>
+
+#include "rtk_common.cuh"
+
+namespace rtk {
+
+constexpr int kMlWarps = 8;
+constexpr int kMlThreads = kMlWarps * kWarp;
+
+struct MallmParams {
+    const __nv_bfloat16* x;          // [T, N, C] input bank (never written)
+    __nv_bfloat16* work;             // [T, N, C] rows rewritten by merges (soft mode only)
+    const __nv_bfloat16* sizes_in;   // [T, N] or null (= ones)
+    int T, N, C;
+    long long si, sp;                // strides of the per-(frame, patch) state arrays
+    float* sim;                      // similarity to the next surviving frame, -inf when there is none
+    float* nrm;                      // clamped bf16 norm of the current row
+    float* size;                     // bf16-valued
+    int* next;                       // T = none
+    int* prev;                       // -1 = none
+    uint8_t* alive;
+    uint8_t* in_work;
+    int* dirty;                      // [2][N][T] rows changed in the previous round
+    int* n_dirty;                    // [2][N]
+    int* merge_at;                   // sync mode: the shared argmax
+    float* msim;                     // [T] sync mode: bf16 mean over patches
+    int* touched;                    // [T] sync mode: stamp of the last round that rewrote sim[i][*]
+    int sync, hard;
+};
+
+__device__ __forceinline__ size_t at(const MallmParams& P, int i, int p) { return (size_t)i * P.si + (size_t)p * P.sp; }
+
+__device__ __forceinline__ const __nv_bfloat16* row_ptr(const MallmParams& P, int i, int p) {
+    const size_t off = ((size_t)i * P.N + p) * (size_t)P.C;
+    return (!P.hard && P.in_work[at(P, i, p)]) ? P.work + off : P.x + off;
+}
+
+// clamp_min_(bf16(1e-8)) of F.cosine_similarity
+__device__ __forceinline__ float clamp_norm(float ss) {
+    return fmaxf(round_bf16(__fsqrt_rn(ss)), __uint_as_float(0x322c0000u));
+}
+__device__ __forceinline__ float warp_tree(float v, int lane) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_down_sync(0xffffffffu, v, off);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
+
+// norm of one row, ATen order with 4-element vectors (lane l owns the 8-byte vectors l, l+32, ...)
+__device__ __forceinline__ float warp_row_norm(const __nv_bfloat16* row, int C, int lane) {
+    const uint2* r = reinterpret_cast<const uint2*>(row);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int v = lane; v < (C >> 2); v += 32) {
+        const uint2 q = r[v];
+        fma_sq_bf16x2(a0, a1, q.x);
+        fma_sq_bf16x2(a2, a3, q.y);
+    }
+    return clamp_norm(warp_tree(((a0 + a1) + a2) + a3, lane));
+}
+
+// bf16 cosine similarity of two rows given their clamped norms, ATen order with 8-element vectors
+__device__ __forceinline__ float warp_pair_sim(const __nv_bfloat16* ra, float na, const __nv_bfloat16* rb, float nb, int C,
+                                               int lane) {
+    const uint4* A = reinterpret_cast<const uint4*>(ra);
+    const uint4* B = reinterpret_cast<const uint4*>(rb);
+    const float ia = __frcp_rn(na), ib = __frcp_rn(nb);      // x * rcp(n) == x / n after the bf16 rounding
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f, c6 = 0.f, c7 = 0.f;
+    for (int v = lane; v < (C >> 3); v += 32) {
+        const uint4 a = A[v], b = B[v];
+        add_bf16x2(c0, c1, mul_bf16x2_rn(scale_bf16x2_rn(a.x, ia), scale_bf16x2_rn(b.x, ib)));
+        add_bf16x2(c2, c3, mul_bf16x2_rn(scale_bf16x2_rn(a.y, ia), scale_bf16x2_rn(b.y, ib)));
+        add_bf16x2(c4, c5, mul_bf16x2_rn(scale_bf16x2_rn(a.z, ia), scale_bf16x2_rn(b.z, ib)));
+        add_bf16x2(c6, c7, mul_bf16x2_rn(scale_bf16x2_rn(a.w, ia), scale_bf16x2_rn(b.w, ib)));
+    }
+    return round_bf16(warp_tree(((((((c0 + c1) + c2) + c3) + c4) + c5) + c6) + c7, lane));
+}
+
+// ---------------------------------------------------------------------------------------------- argmax
+struct Best {
+    float v;
+    int i;
+};
+// torch.max(dim) on CUDA: NaN is the maximum, equal values go to the lowest index
+__device__ __forceinline__ bool better(const Best& a, const Best& b) {
+    const bool an = a.v != a.v, bn = b.v != b.v;
+    if (an || bn) return (an && bn) ? a.i < b.i : an;
+    return (a.v != b.v) ? a.v > b.v : a.i < b.i;
+}
+// argmax over v[i * stride], i < T; the result is valid in every thread.  `scratch` holds one Best per warp.
+__device__ __forceinline__ int block_argmax(const float* v, long long stride, int T, Best* scratch) {
+    Best b{-INFINITY, 0x7fffffff};
+    for (int i = threadIdx.x; i < T; i += blockDim.x) {
+        const Best c{v[(size_t)i * stride], i};
+        if (better(c, b)) b = c;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        Best o{__shfl_down_sync(0xffffffffu, b.v, off), __shfl_down_sync(0xffffffffu, b.i, off)};
+        if (better(o, b)) b = o;
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    if (lane == 0) scratch[warp] = b;
+    __syncthreads();
+    if (warp == 0) {
+        b = (lane < nw) ? scratch[lane] : Best{-INFINITY, 0x7fffffff};
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            Best o{__shfl_down_sync(0xffffffffu, b.v, off), __shfl_down_sync(0xffffffffu, b.i, off)};
+            if (better(o, b)) b = o;
+        }
+        if (lane == 0) scratch[0] = b;
+    }
+    __syncthreads();
+    const int r = scratch[0].i;
+    __syncthreads();
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------------ init
+// one CTA per patch: norms, sizes, links, all adjacent similarities
+__global__ void __launch_bounds__(kMlThreads) mallm_init_kernel(MallmParams P) {
+    __shared__ int s_cnt;
+    const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = warp; i < P.T; i += kMlWarps) {
+        const float n = warp_row_norm(P.x + ((size_t)i * P.N + p) * (size_t)P.C, P.C, lane);
+        if (lane == 0) {
+            const size_t a = at(P, i, p);
+            P.nrm[a] = n;
+            P.next[a] = i + 1;
+            P.prev[a] = i - 1;
+            P.alive[a] = 1;
+            if (!P.hard) {
+                const float s = P.sizes_in ? __bfloat162float(P.sizes_in[(size_t)i * P.N + p]) : 1.0f;
+                P.size[a] = s;
+                P.in_work[a] = 0;
+                if (s != 1.0f) P.dirty[(size_t)p * P.T + atomicAdd(&s_cnt, 1)] = i;   // not known to be a fixed point
+            }
+            if (P.sync && p == 0) P.touched[i] = 0;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && !P.hard) P.n_dirty[p] = s_cnt;
+    for (int i = warp; i < P.T; i += kMlWarps) {
+        float s = -INFINITY;
+        if (i + 1 < P.T) {
+            const __nv_bfloat16* ra = P.x + ((size_t)i * P.N + p) * (size_t)P.C;
+            s = warp_pair_sim(ra, P.nrm[at(P, i, p)], ra + (size_t)P.N * P.C, P.nrm[at(P, i + 1, p)], P.C, lane);
+        }
+        if (lane == 0) P.sim[at(P, i, p)] = s;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------- round
+__device__ __forceinline__ uint32_t merge_pair(uint32_t a, uint32_t b, float sa, float sb, float snew) {
+    const float lo = round_bf16(__fdiv_rn(round_bf16(round_bf16(bf16lo_to_f32(a) * sa) + round_bf16(bf16lo_to_f32(b) * sb)), snew));
+    const float hi = round_bf16(__fdiv_rn(round_bf16(round_bf16(bf16hi_to_f32(a) * sa) + round_bf16(bf16hi_to_f32(b) * sb)), snew));
+    return pack_bf16x2_rn(lo, hi);
+}
+__device__ __forceinline__ uint32_t rescale_pair(uint32_t a, float s) {
+    const float lo = __fdiv_rn(round_bf16(bf16lo_to_f32(a) * s), s);
+    const float hi = __fdiv_rn(round_bf16(bf16hi_to_f32(a) * s), s);
+    return pack_bf16x2_rn(lo, hi);
+}
+
+// soft merge: one CTA per patch, `round` = number of merges already done
+__global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, int round) {
+    __shared__ Best s_best[kMlWarps];
+    __shared__ int s_m, s_n, s_cnt;
+    const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = P.T, C = P.C;
+    const int m = P.sync ? P.merge_at[0] : block_argmax(P.sim + (size_t)p * P.sp, P.si, T, s_best);
+    if (threadIdx.x == 0) {
+        s_m = m;
+        s_n = P.next[at(P, m, p)];
+        s_cnt = 0;
+    }
+    __syncthreads();
+    const int n = s_n;
+    const int* cur = P.dirty + ((size_t)(round & 1) * P.N + p) * T;
+    int* nxt = P.dirty + ((size_t)((round + 1) & 1) * P.N + p) * T;
+    const int nd = P.n_dirty[(size_t)(round & 1) * P.N + p];
+    const size_t row_elems = (size_t)C;
+    // ---- row tasks: task 0 merges (m, n) into m; task k > 0 replays x = rd(rd(x * s) / s) on a dirty row
+    for (int task = warp; task <= nd; task += kMlWarps) {
+        const int j = task ? cur[task - 1] : m;
+        if (task && (j == m || j == n)) continue;
+        const size_t a = at(P, j, p);
+        const uint2* src = reinterpret_cast<const uint2*>(row_ptr(P, j, p));
+        uint2* dst = reinterpret_cast<uint2*>(P.work + ((size_t)j * P.N + p) * row_elems);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        bool changed = true;
+        if (task == 0) {
+            const uint2* src2 = reinterpret_cast<const uint2*>(row_ptr(P, n, p));
+            const float sa = P.size[a], sb = P.size[at(P, n, p)];
+            const float snew = round_bf16(sa + sb);
+            for (int v = lane; v < (C >> 2); v += 32) {
+                const uint2 q = src[v], r = src2[v];
+                uint2 y;
+                y.x = merge_pair(q.x, r.x, sa, sb, snew);
+                y.y = merge_pair(q.y, r.y, sa, sb, snew);
+                dst[v] = y;
+                fma_sq_bf16x2(a0, a1, y.x);
+                fma_sq_bf16x2(a2, a3, y.y);
+            }
+            if (lane == 0) P.size[a] = snew;
+        } else {
+            const float s = P.size[a];
+            bool diff = false;
+            for (int v = lane; v < (C >> 2); v += 32) {
+                const uint2 q = src[v];
+                uint2 y;
+                y.x = rescale_pair(q.x, s);
+                y.y = rescale_pair(q.y, s);
+                diff |= (y.x != q.x) || (y.y != q.y);
+                dst[v] = y;
+                fma_sq_bf16x2(a0, a1, y.x);
+                fma_sq_bf16x2(a2, a3, y.y);
+            }
+            changed = __any_sync(0xffffffffu, diff);
+        }
+        const float nr = clamp_norm(warp_tree(((a0 + a1) + a2) + a3, lane));
+        if (lane == 0) {
+            P.nrm[a] = nr;
+            P.in_work[a] = 1;
+            if (changed) nxt[atomicAdd(&s_cnt, 1)] = j;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                                      // unlink n
+        const int nx = P.next[at(P, n, p)];
+        P.next[at(P, m, p)] = nx;
+        if (nx < T) P.prev[at(P, nx, p)] = m;
+        P.alive[at(P, n, p)] = 0;
+        P.sim[at(P, n, p)] = -INFINITY;
+        if (P.sync && p == 0) P.touched[n] = round + 1;
+        P.n_dirty[(size_t)((round + 1) & 1) * P.N + p] = s_cnt;
+    }
+    __syncthreads();
+    // ---- similarities on both sides of every changed row
+    const int nch = s_cnt;
+    for (int task = warp; task < 2 * nch; task += kMlWarps) {
+        const int j = nxt[task >> 1];
+        int a, b;
+        if (task & 1) { a = j; b = P.next[at(P, j, p)]; }
+        else { a = P.prev[at(P, j, p)]; b = j; }
+        if (a < 0) continue;
+        float s = -INFINITY;
+        if (b < T) s = warp_pair_sim(row_ptr(P, a, p), P.nrm[at(P, a, p)], row_ptr(P, b, p), P.nrm[at(P, b, p)], C, lane);
+        if (lane == 0) {
+            P.sim[at(P, a, p)] = s;
+            if (P.sync) P.touched[a] = round + 1;
+        }
+    }
+}
+
+// hard variant: frame m is deleted, nothing is rewritten
+__global__ void __launch_bounds__(kMlThreads) mallm_hard_round_kernel(MallmParams P, int round) {
+    __shared__ Best s_best[kMlWarps];
+    const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = P.T;
+    const int m = P.sync ? P.merge_at[0] : block_argmax(P.sim + (size_t)p * P.sp, P.si, T, s_best);
+    if (warp != 0) return;
+    const int pm = P.prev[at(P, m, p)], n = P.next[at(P, m, p)];
+    float s = 0.f;
+    if (pm >= 0) s = warp_pair_sim(row_ptr(P, pm, p), P.nrm[at(P, pm, p)], row_ptr(P, n, p), P.nrm[at(P, n, p)], P.C, lane);
+    if (lane == 0) {
+        P.alive[at(P, m, p)] = 0;
+        P.sim[at(P, m, p)] = -INFINITY;
+        P.prev[at(P, n, p)] = pm;
+        if (pm >= 0) {
+            P.next[at(P, pm, p)] = n;
+            P.sim[at(P, pm, p)] = s;
+        }
+        if (P.sync && p == 0) {
+            P.touched[m] = round + 1;
+            if (pm >= 0) P.touched[pm] = round + 1;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------- sync mode: mean + argmax
+// ATen's bf16 mean(-1) over n contiguous values (held as fp32), times fp32(1/n) and rounded by the caller.
+// `shift` = (byte offset of the row in the reference's bf16 tensor % 16) / 2.  Result valid in lane 0.
+__device__ __forceinline__ float aten_row_sum_bf16(const float* __restrict__ row, int n, int shift, int lane) {
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int width = 1, nacc = 8;
+    if (n >= 128) {
+        while (width * 2 <= (n >> 3) && width < 32) width *= 2;
+        int start = 0;
+        if (shift > 0) {
+            if (lane >= shift && lane < 8) a[0] += row[lane - shift];
+            start = 8 - shift;
+        }
+        const int body = (n - start) >> 3;
+        if (lane < width)
+            for (int idx = lane; idx < body; idx += width) {
+                const float* q = row + start + idx * 8;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] += q[j];
+            }
+        const int tail = start + body * 8 + lane;
+        if (tail < n) a[0] += row[tail];
+    } else {
+        nacc = 4;
+        while (width * 2 <= n && width < 32) width *= 2;
+        if (lane < width) {
+            int k = 0;
+            for (int idx = lane; idx < n; idx += width, k = (k + 1) & 3) a[k] += row[idx];
+        }
+    }
+    float s = ((a[0] + a[1]) + a[2]) + a[3];
+    if (nacc == 8) s = (((s + a[4]) + a[5]) + a[6]) + a[7];
+    for (int off = width >> 1; off > 0; off >>= 1) s += __shfl_down_sync(0xffffffffu, s, off);
+    return s;
+}
+
+// one CTA: refresh the mean similarity of the rows rewritten in the round stamped `stamp` (all rows when the row
+// alignment depends on the position, i.e. N % 8 != 0), then the shared argmax
+__global__ void __launch_bounds__(1024) mallm_sync_argmax_kernel(MallmParams P, int stamp) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    int* pos = reinterpret_cast<int*>(smem_raw);                 // [T] index of frame i among the survivors
+    __shared__ int s_warp_tot[32];
+    __shared__ Best s_best[32];
+    const int T = P.T, N = P.N;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    const bool all = (N & 7) != 0 || stamp == 0;
+    if (all && N >= 128 && (N & 7)) {
+        // exclusive scan of the alive flags, chunk per thread
+        const int per = (T + blockDim.x - 1) / blockDim.x;
+        const int i0 = threadIdx.x * per, i1 = min(T, i0 + per);
+        int cnt = 0;
+        for (int i = i0; i < i1; ++i) cnt += P.alive[at(P, i, 0)];
+        int inc = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += o;
+        }
+        if (lane == 31) s_warp_tot[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int t = (lane < nw) ? s_warp_tot[lane] : 0;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, t, off);
+                if (lane >= off) t += o;
+            }
+            s_warp_tot[lane] = t;
+        }
+        __syncthreads();
+        int run = inc - cnt + (warp ? s_warp_tot[warp - 1] : 0);
+        for (int i = i0; i < i1; ++i) {
+            pos[i] = run;
+            run += P.alive[at(P, i, 0)];
+        }
+        __syncthreads();
+    }
+    const float rcp = 1.0f / (float)N;
+    for (int i = warp; i < T; i += nw) {
+        if (!all && P.touched[i] != stamp) continue;
+        const float* row = P.sim + (size_t)i * P.si;
+        float v = -INFINITY;
+        if (row[0] != -INFINITY) {                               // dead and last rows hold -inf in every patch
+            const int shift = (N >= 128 && (N & 7)) ? (int)(((long long)pos[i] * N) & 7) : 0;
+            v = round_bf16(aten_row_sum_bf16(row, N, shift, lane) * rcp);
+        }
+        if (lane == 0) P.msim[i] = v;
+    }
+    __syncthreads();
+    const int m = block_argmax(P.msim, 1, T, s_best);
+    if (threadIdx.x == 0) P.merge_at[0] = m;
+}
+
+// --------------------------------------------------------------------------------------------- compaction
+// one CTA per patch: surviving rows in frame order -> out[pos, p, :], sizes_out[pos, p]
+__global__ void __launch_bounds__(kMlThreads) mallm_emit_kernel(MallmParams P, __nv_bfloat16* __restrict__ out,
+                                                               __nv_bfloat16* __restrict__ sizes_out, int t) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    int* order = reinterpret_cast<int*>(smem_raw);               // [t]
+    __shared__ int s_warp_tot[kMlWarps];
+    const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T = P.T;
+    const int per = (T + kMlThreads - 1) / kMlThreads;
+    const int i0 = threadIdx.x * per, i1 = min(T, i0 + per);
+    int cnt = 0;
+    for (int i = i0; i < i1; ++i) cnt += P.alive[at(P, i, p)];
+    int inc = cnt;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += o;
+    }
+    if (lane == 31) s_warp_tot[warp] = inc;
+    __syncthreads();
+    int base = inc - cnt;
+    for (int w = 0; w < warp; ++w) base += s_warp_tot[w];
+    for (int i = i0; i < i1; ++i)
+        if (P.alive[at(P, i, p)]) {
+            if (base < t) order[base] = i;
+            ++base;
+        }
+    __syncthreads();
+    const int nvec = P.C >> 3;
+    for (int j = warp; j < t; j += kMlWarps) {
+        const int i = order[j];
+        const uint4* src = reinterpret_cast<const uint4*>(row_ptr(P, i, p));
+        uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)j * P.N + p) * (size_t)P.C);
+        for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
+        if (lane == 0 && sizes_out) sizes_out[(size_t)j * P.N + p] = __float2bfloat16_rn(P.size[at(P, i, p)]);
+    }
+}
+
+static size_t align_up(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct MallmLayout {
+    size_t sim, nrm, size, next, prev, alive, in_work, dirty, n_dirty, merge_at, msim, touched, work, total;
+};
+static MallmLayout mallm_layout(int64_t T, int64_t N, int64_t C, int hard) {
+    MallmLayout L;
+    const size_t tn = (size_t)T * N;
+    size_t o = 0;
+    L.sim = o; o = align_up(o + tn * 4);
+    L.nrm = o; o = align_up(o + tn * 4);
+    L.size = o; o = align_up(o + tn * 4);
+    L.next = o; o = align_up(o + tn * 4);
+    L.prev = o; o = align_up(o + tn * 4);
+    L.alive = o; o = align_up(o + tn);
+    L.in_work = o; o = align_up(o + tn);
+    L.dirty = o; o = align_up(o + 2 * tn * 4);
+    L.n_dirty = o; o = align_up(o + 2 * (size_t)N * 4);
+    L.merge_at = o; o = align_up(o + 4);
+    L.msim = o; o = align_up(o + (size_t)T * 4);
+    L.touched = o; o = align_up(o + (size_t)T * 4);
+    L.work = o; o = align_up(o + (hard ? 0 : tn * (size_t)C * 2));
+    L.total = o;
+    return L;
+}
+
+}  // namespace rtk
+
+using namespace rtk;
+
+extern "C" size_t rtk_mallm_workspace_bytes(int64_t T, int64_t N, int64_t C, int hard) {
+    if (T <= 0 || N <= 0 || C <= 0) return 0;
+    return mallm_layout(T, N, C, hard).total;
+}
+
+extern "C" int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T, int64_t N, int64_t C, int64_t t, int sync,
+                                  int hard, void* out, void* sizes_out, void* workspace, size_t workspace_bytes,
+                                  void* stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!x || !out || !workspace || T < 1 || N < 1 || t < 1 || t > T) return RTK_E_BADARG;
+    if (C % 8 != 0 || C < 256 || C > 8160 || T > 8192 || N > 65535) return RTK_E_UNSUPPORTED;
+    if (((uintptr_t)x | (uintptr_t)out | (uintptr_t)workspace) & 15u) return RTK_E_ALIGN;
+    const MallmLayout L = mallm_layout(T, N, C, hard);
+    if (workspace_bytes < L.total) return RTK_E_WORKSPACE;
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    MallmParams P;
+    P.x = static_cast<const __nv_bfloat16*>(x);
+    P.work = reinterpret_cast<__nv_bfloat16*>(ws + L.work);
+    P.sizes_in = static_cast<const __nv_bfloat16*>(sizes_in);
+    P.T = (int)T; P.N = (int)N; P.C = (int)C;
+    // the shared argmax of sync mode reads one frame across patches, the per-patch argmax one patch across frames
+    P.si = sync ? N : 1;
+    P.sp = sync ? 1 : T;
+    P.sim = reinterpret_cast<float*>(ws + L.sim);
+    P.nrm = reinterpret_cast<float*>(ws + L.nrm);
+    P.size = reinterpret_cast<float*>(ws + L.size);
+    P.next = reinterpret_cast<int*>(ws + L.next);
+    P.prev = reinterpret_cast<int*>(ws + L.prev);
+    P.alive = ws + L.alive;
+    P.in_work = ws + L.in_work;
+    P.dirty = reinterpret_cast<int*>(ws + L.dirty);
+    P.n_dirty = reinterpret_cast<int*>(ws + L.n_dirty);
+    P.merge_at = reinterpret_cast<int*>(ws + L.merge_at);
+    P.msim = reinterpret_cast<float*>(ws + L.msim);
+    P.touched = reinterpret_cast<int*>(ws + L.touched);
+    P.sync = sync ? 1 : 0;
+    P.hard = hard ? 1 : 0;
+    const size_t scan_smem = (size_t)T * 4;
+    if (sync) {
+        cudaError_t e = cudaFuncSetAttribute(mallm_sync_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    mallm_init_kernel<<<(unsigned)N, kMlThreads, 0, stream>>>(P);
+    RTK_CHECK_LAUNCH();
+    if (sync && t < T) {
+        mallm_sync_argmax_kernel<<<1, 1024, scan_smem, stream>>>(P, 0);
+        RTK_CHECK_LAUNCH();
+    }
+    for (int r = 0; r < (int)(T - t); ++r) {
+        if (hard) mallm_hard_round_kernel<<<(unsigned)N, kMlThreads, 0, stream>>>(P, r);
+        else mallm_round_kernel<<<(unsigned)N, kMlThreads, 0, stream>>>(P, r);
+        RTK_CHECK_LAUNCH();
+        if (sync && r + 1 < (int)(T - t)) {
+            mallm_sync_argmax_kernel<<<1, 1024, scan_smem, stream>>>(P, r + 1);
+            RTK_CHECK_LAUNCH();
+        }
+    }
+    const size_t emit_smem = (size_t)t * 4;
+    cudaError_t e = cudaFuncSetAttribute(mallm_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem);
+    if (e != cudaSuccess) return (int)e;
+    mallm_emit_kernel<<<(unsigned)N, kMlThreads, emit_smem, stream>>>(P, static_cast<__nv_bfloat16*>(out),
+                                                                    hard ? nullptr : static_cast<__nv_bfloat16*>(sizes_out), (int)t);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}

@@ -24,7 +24,7 @@ from transformers.models.llava_onevision import modeling_llava_onevision as hf
 from transformers.models.qwen2 import modeling_qwen2 as hfq
 
 from .longvideo_cache import PivotKVCache, build_kvcache
-from .visual_compression import memory_bank_compress_keyframe
+from .visual_compression import mallm_compress, memory_bank_compress_keyframe
 
 __all__ = ["install", "uninstall", "retake_Qwen2Attention_init", "retake_Qwen2Attention_forward",
            "retake_LlavaOnevisionModel_forward",
@@ -132,8 +132,11 @@ def retake_LlavaOnevisionForConditionalGeneration_compress_video_tokens(self, in
         if kw.get("compression_method") == "Keyframe":
             bank, keypatches_mask = memory_bank_compress_keyframe(bank, tgt_grid_t, 3, sync=kw.get("patch_sync"))
             keypatches_mask = keypatches_mask if kw.get("return_keyframe_mask") else None
+        elif kw.get("compression_method") in ("MA-LLM", "MA-LLM-hard"):   # llava_onevision.py:235-243, fused
+            bank, _ = mallm_compress(bank, tgt_grid_t, sync=bool(kw.get("patch_sync")),
+                                     hard=kw.get("compression_method") == "MA-LLM-hard")
         else:
-            raise NotImplementedError(f"visual compression method {kw.get('compression_method')!r} is outside the B200 hot path")
+            raise NotImplementedError(f"unknown visual compression method {kw.get('compression_method')!r}")
         selected_video_feature = bank[0]
         mem_len_after = tgt_grid_t * grid_hw_after_pool
         input_ids = torch.cat([input_ids[:, :s_index], input_ids[:, s_index:e_index + 1][:, :mem_len_after],

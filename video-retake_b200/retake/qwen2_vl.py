@@ -31,7 +31,7 @@ import torch
 from transformers.models.qwen2_vl import modeling_qwen2_vl as hf
 
 from .longvideo_cache import PivotKVCache, build_kvcache
-from .visual_compression import memory_bank_compress_keyframe
+from .visual_compression import mallm_compress, memory_bank_compress_keyframe
 
 __all__ = ["install", "retake_Qwen2VLAttention_forward", "retake_Qwen2VLModel_forward",
            "retake_Qwen2VLForConditionalGeneration_compress_video_tokens",
@@ -133,8 +133,10 @@ def retake_Qwen2VLForConditionalGeneration_compress_video_tokens(self, input_ids
         if method == "Keyframe":
             bank, keypatches_mask = memory_bank_compress_keyframe(bank, tgt_mem_len, 3, sync=kw.get("patch_sync"))
             keypatches_mask = keypatches_mask if kw.get("return_keyframe_mask") else None
+        elif method in ("MA-LLM", "MA-LLM-hard"):                   # the reference's while-loop (qwen2_vl.py:402-409), fused
+            bank, _ = mallm_compress(bank, tgt_mem_len, sync=bool(kw.get("patch_sync")), hard=method == "MA-LLM-hard")
         else:
-            raise NotImplementedError(f"visual compression method {method!r} is outside the B200 hot path")
+            raise NotImplementedError(f"unknown visual compression method {method!r}")
         video_embeds = bank.flatten(1, 2)[0]
         tgt_seq_len = video_embeds.shape[0]
         input_ids = torch.cat([input_ids[:, :s_index], input_ids[:, s_index:e_index + 1][:, :tgt_seq_len],

@@ -8,8 +8,9 @@ C ABI (``include/rtk_b200.h``) on the current CUDA stream, with no host synchron
     rtk_dpselect_select  peaks, +2 priority, top-t, ascending sort (lines 108-135 / 141-169,175)
     rtk_dpselect_gather  compaction of the surviving tokens        (lines 138 / 173)
 
-The alternative compressors of the reference (``memory_bank_compress_MALLM*``, lines 5-83) are not
-selected by any shipped config and are out of scope of this path.
+The alternative compressors of the reference (``memory_bank_compress_MALLM*``, lines 5-83; ``compression_method:
+MA-LLM / MA-LLM-hard``) run on ``rtk_mallm_compress``: the single-round functions keep the reference's signatures,
+``mallm_compress`` is the caller's whole ``while T > tgt`` loop (``qwen2_vl.py:402-409``) in one library call.
 """
 from __future__ import annotations
 
@@ -18,7 +19,7 @@ import torch
 from . import _native as N
 
 __all__ = ["memory_bank_compress_keyframe", "dpselect_distance", "dpselect_select", "dpselect_gather",
-           "memory_bank_compress_MALLM", "memory_bank_compress_MALLM_hard"]
+           "memory_bank_compress_MALLM", "memory_bank_compress_MALLM_hard", "mallm_compress"]
 
 
 def dpselect_distance(x: torch.Tensor, halo: bool = False) -> torch.Tensor:
@@ -94,9 +95,48 @@ def memory_bank_compress_keyframe(memory_bank: torch.Tensor, tgt_mem_len: int, w
     return out, mask
 
 
-def memory_bank_compress_MALLM(*args, **kwargs):
-    raise NotImplementedError("MA-LLM compression is outside the B200 hot path (SURVEY.md section 2, row 6)")
+def mallm_compress(memory_bank: torch.Tensor, tgt_mem_len: int, compression_size: torch.Tensor = None, sync: bool = False,
+                   hard: bool = False):
+    """``memory_bank[1, T, N, C]`` bf16 -> ``([1, t, N, C], sizes [1, t, N] or None)``: the reference's
+    ``while bank.shape[1] > tgt_mem_len: bank(, size) = memory_bank_compress_MALLM[_hard](bank(, size), sync)`` loop
+    (``qwen2_vl.py:402-409``, ``llava_onevision.py:235-243``) as one fused call, bit-identical for bf16 banks."""
+    N.require_cuda(memory_bank, "memory_bank", torch.bfloat16)
+    if memory_bank.dim() != 4 or memory_bank.shape[0] != 1:
+        raise ValueError("expected memory_bank [1, T, N, C] (the reference only runs batch 1)")
+    _, T, Np, Cc = memory_bank.shape
+    t = min(int(tgt_mem_len), T)                               # the loop does nothing once T <= tgt
+    if t < 1:
+        raise ValueError("tgt_mem_len must be >= 1")
+    x = memory_bank[0].contiguous()
+    sizes_in = None
+    if compression_size is not None and not hard:
+        N.require_cuda(compression_size, "compression_size", torch.bfloat16)
+        if tuple(compression_size.shape) != (1, T, Np):
+            raise ValueError("compression_size must be [1, T, N]")
+        sizes_in = compression_size[0].contiguous()
+    out = torch.empty((1, t, Np, Cc), dtype=x.dtype, device=x.device)
+    sizes_out = None if hard else torch.empty((1, t, Np), dtype=x.dtype, device=x.device)
+    lib = N.lib()
+    ws_bytes = lib.rtk_mallm_workspace_bytes(T, Np, Cc, int(hard))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        N.check(lib.rtk_mallm_compress(x.data_ptr(), sizes_in.data_ptr() if sizes_in is not None else None, T, Np, Cc, t,
+                                       int(bool(sync)), int(bool(hard)), out.data_ptr(),
+                                       sizes_out.data_ptr() if sizes_out is not None else None, ws.data_ptr(), ws_bytes,
+                                       N.stream_ptr(x.device)), "rtk_mallm_compress")
+    return out, sizes_out
 
 
-def memory_bank_compress_MALLM_hard(*args, **kwargs):
-    raise NotImplementedError("MA-LLM-hard compression is outside the B200 hot path (SURVEY.md section 2, row 6)")
+def memory_bank_compress_MALLM(memory_bank: torch.Tensor, compression_size: torch.Tensor, sync: bool = False):
+    """One merge of the most similar adjacent frame pair (``visual_compression.py:5-47``):
+    ``([1, T, N, C], [1, T, N]) -> ([1, T-1, N, C], [1, T-1, N])``."""
+    if memory_bank.shape[1] < 2:
+        raise ValueError("MA-LLM needs at least two frames")
+    return mallm_compress(memory_bank, memory_bank.shape[1] - 1, compression_size, sync=sync, hard=False)
+
+
+def memory_bank_compress_MALLM_hard(memory_bank: torch.Tensor, sync: bool = False):
+    """One deletion of the first frame of the most similar adjacent pair (``visual_compression.py:50-83``)."""
+    if memory_bank.shape[1] < 2:
+        raise ValueError("MA-LLM needs at least two frames")
+    return mallm_compress(memory_bank, memory_bank.shape[1] - 1, None, sync=sync, hard=True)[0]
