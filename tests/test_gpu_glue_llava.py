@@ -92,3 +92,17 @@ def test_compressed_prefill_and_generate(patched, reforge):
     with torch.no_grad():
         out_ids = model.generate(**inp, max_new_tokens=4, generation_config=gen_cfg)
     assert out_ids.shape[1] == inp["input_ids"].shape[1] + 4
+
+
+@pytest.mark.parametrize("method", ["MA-LLM", "MA-LLM-hard"])
+def test_mallm_visual_compression_methods(patched, method):
+    """`compression_method: MA-LLM / MA-LLM-hard` (llava_onevision.py:235-243) through the fused loop"""
+    model = tiny_model()
+    kw = lv_kwargs(vis=True, rv=0.5, kv=True, rkv=0.5, reforge=False)
+    kw["visual_compression_kwargs"]["compression_method"] = method
+    model.config.longvideo_kwargs = kw
+    with torch.no_grad():
+        o = model(**make_inputs(), use_cache=True)
+    want_len = 5 + 2 * 8 + 6
+    assert [o.past_key_values.get_seq_length(l) for l in range(2)] == [want_len, want_len]
+    assert torch.isfinite(o.logits.float()).all()

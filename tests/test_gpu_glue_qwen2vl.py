@@ -127,3 +127,26 @@ def test_compressed_prefill_and_generate(patched, reforge):
     with torch.no_grad():
         out_ids = model.generate(**inp, max_new_tokens=4, generation_config=gen_cfg)
     assert out_ids.shape[1] == inp["input_ids"].shape[1] + 4
+
+
+@pytest.mark.parametrize("method", ["MA-LLM", "MA-LLM-hard"])
+def test_mallm_visual_compression_methods(patched, method):
+    """`compression_method: MA-LLM / MA-LLM-hard` (qwen2_vl.py:402-409): the fused loop feeds the same chunked prefill."""
+    from oracle import reference_ops as ro
+    model = tiny_model()
+    inp = make_inputs()
+    kw = lv_kwargs(rv=0.5, rkv=0.5, chunk_frames=8)
+    kw["visual_compression_kwargs"]["compression_method"] = method
+    model.config.longvideo_kwargs = kw
+    emb = torch.randn(16 * 16, model.config.text_config.hidden_size if hasattr(model.config, "text_config") else model.config.hidden_size,
+                      generator=torch.Generator().manual_seed(5)).to(torch.bfloat16).cuda()
+    ids, _, vid, _, _, _, mask = model.compress_video_tokens(input_ids=inp["input_ids"], attention_mask=inp["attention_mask"],
+                                                             video_embeds=emb, video_grid_thw=torch.tensor([[16, 8, 8]]).cuda())
+    want, _ = ro.mallm_compress(emb.reshape(1, 16, 16, -1).clone(), 8, False, method == "MA-LLM-hard")
+    assert mask is None and torch.equal(vid, want.flatten(1, 2)[0])
+    assert ids.shape[1] == inp["input_ids"].shape[1] - 8 * 16
+    with torch.no_grad():
+        o = model(**inp, use_cache=True)
+    want_len = 6 + 2 * 32 + 7
+    assert [o.past_key_values.get_seq_length(l) for l in range(2)] == [want_len, want_len]
+    assert torch.isfinite(o.logits.float()).all()

@@ -64,11 +64,28 @@ __device__ __forceinline__ float warp_tree(float v, int lane) {
     return __shfl_sync(0xffffffffu, v, 0);
 }
 
+// Rows live in HBM / L2 and every loop below is a chain of dependent round trips unless the loads are issued in
+// batches: kBatch independent vector loads per lane are in flight before the first one is consumed.  The order in
+// which values enter the accumulators is unchanged (ascending vector index per lane).
+constexpr int kBatch = 8;
+
 // norm of one row, ATen order with 4-element vectors (lane l owns the 8-byte vectors l, l+32, ...)
 __device__ __forceinline__ float warp_row_norm(const __nv_bfloat16* row, int C, int lane) {
     const uint2* r = reinterpret_cast<const uint2*>(row);
+    const int nv = C >> 2;
     float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    for (int v = lane; v < (C >> 2); v += 32) {
+    int v = lane;
+    for (; v + (kBatch - 1) * 32 < nv; v += kBatch * 32) {
+        uint2 q[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) q[u] = r[v + 32 * u];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+            fma_sq_bf16x2(a0, a1, q[u].x);
+            fma_sq_bf16x2(a2, a3, q[u].y);
+        }
+    }
+    for (; v < nv; v += 32) {
         const uint2 q = r[v];
         fma_sq_bf16x2(a0, a1, q.x);
         fma_sq_bf16x2(a2, a3, q.y);
@@ -81,15 +98,25 @@ __device__ __forceinline__ float warp_pair_sim(const __nv_bfloat16* ra, float na
                                                int lane) {
     const uint4* A = reinterpret_cast<const uint4*>(ra);
     const uint4* B = reinterpret_cast<const uint4*>(rb);
+    const int nv = C >> 3;
     const float ia = __frcp_rn(na), ib = __frcp_rn(nb);      // x * rcp(n) == x / n after the bf16 rounding
     float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f, c6 = 0.f, c7 = 0.f;
-    for (int v = lane; v < (C >> 3); v += 32) {
-        const uint4 a = A[v], b = B[v];
+    auto step = [&](const uint4& a, const uint4& b) {
         add_bf16x2(c0, c1, mul_bf16x2_rn(scale_bf16x2_rn(a.x, ia), scale_bf16x2_rn(b.x, ib)));
         add_bf16x2(c2, c3, mul_bf16x2_rn(scale_bf16x2_rn(a.y, ia), scale_bf16x2_rn(b.y, ib)));
         add_bf16x2(c4, c5, mul_bf16x2_rn(scale_bf16x2_rn(a.z, ia), scale_bf16x2_rn(b.z, ib)));
         add_bf16x2(c6, c7, mul_bf16x2_rn(scale_bf16x2_rn(a.w, ia), scale_bf16x2_rn(b.w, ib)));
+    };
+    constexpr int kHalf = kBatch / 2;
+    int v = lane;
+    for (; v + (kHalf - 1) * 32 < nv; v += kHalf * 32) {
+        uint4 a[kHalf], b[kHalf];
+#pragma unroll
+        for (int u = 0; u < kHalf; ++u) { a[u] = A[v + 32 * u]; b[u] = B[v + 32 * u]; }
+#pragma unroll
+        for (int u = 0; u < kHalf; ++u) step(a[u], b[u]);
     }
+    for (; v < nv; v += 32) step(A[v], B[v]);
     return round_bf16(warp_tree(((((((c0 + c1) + c2) + c3) + c4) + c5) + c6) + c7, lane));
 }
 
@@ -209,25 +236,34 @@ __global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, 
         uint2* dst = reinterpret_cast<uint2*>(P.work + ((size_t)j * P.N + p) * row_elems);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
         bool changed = true;
+        const int nv = C >> 2;
         if (task == 0) {
             const uint2* src2 = reinterpret_cast<const uint2*>(row_ptr(P, n, p));
             const float sa = P.size[a], sb = P.size[at(P, n, p)];
             const float snew = round_bf16(sa + sb);
-            for (int v = lane; v < (C >> 2); v += 32) {
-                const uint2 q = src[v], r = src2[v];
+            auto step = [&](int v, const uint2& q, const uint2& r) {
                 uint2 y;
                 y.x = merge_pair(q.x, r.x, sa, sb, snew);
                 y.y = merge_pair(q.y, r.y, sa, sb, snew);
                 dst[v] = y;
                 fma_sq_bf16x2(a0, a1, y.x);
                 fma_sq_bf16x2(a2, a3, y.y);
+            };
+            constexpr int kHalf = kBatch / 2;
+            int v = lane;
+            for (; v + (kHalf - 1) * 32 < nv; v += kHalf * 32) {
+                uint2 q[kHalf], r[kHalf];
+#pragma unroll
+                for (int u = 0; u < kHalf; ++u) { q[u] = src[v + 32 * u]; r[u] = src2[v + 32 * u]; }
+#pragma unroll
+                for (int u = 0; u < kHalf; ++u) step(v + 32 * u, q[u], r[u]);
             }
+            for (; v < nv; v += 32) step(v, src[v], src2[v]);
             if (lane == 0) P.size[a] = snew;
         } else {
             const float s = P.size[a];
             bool diff = false;
-            for (int v = lane; v < (C >> 2); v += 32) {
-                const uint2 q = src[v];
+            auto step = [&](int v, const uint2& q) {
                 uint2 y;
                 y.x = rescale_pair(q.x, s);
                 y.y = rescale_pair(q.y, s);
@@ -235,7 +271,16 @@ __global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, 
                 dst[v] = y;
                 fma_sq_bf16x2(a0, a1, y.x);
                 fma_sq_bf16x2(a2, a3, y.y);
+            };
+            int v = lane;
+            for (; v + (kBatch - 1) * 32 < nv; v += kBatch * 32) {
+                uint2 q[kBatch];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) q[u] = src[v + 32 * u];
+#pragma unroll
+                for (int u = 0; u < kBatch; ++u) step(v + 32 * u, q[u]);
             }
+            for (; v < nv; v += 32) step(v, src[v]);
             changed = __any_sync(0xffffffffu, diff);
         }
         const float nr = clamp_norm(warp_tree(((a0 + a1) + a2) + a3, lane));
@@ -425,7 +470,15 @@ __global__ void __launch_bounds__(kMlThreads) mallm_emit_kernel(MallmParams P, _
         const int i = order[j];
         const uint4* src = reinterpret_cast<const uint4*>(row_ptr(P, i, p));
         uint4* dst = reinterpret_cast<uint4*>(out + ((size_t)j * P.N + p) * (size_t)P.C);
-        for (int v = lane; v < nvec; v += 32) dst[v] = src[v];
+        int v = lane;
+        for (; v + (kBatch - 1) * 32 < nvec; v += kBatch * 32) {
+            uint4 b[kBatch];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) b[u] = src[v + 32 * u];
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) dst[v + 32 * u] = b[u];
+        }
+        for (; v < nvec; v += 32) dst[v] = src[v];
         if (lane == 0 && sizes_out) sizes_out[(size_t)j * P.N + p] = __float2bfloat16_rn(P.size[at(P, i, p)]);
     }
 }
