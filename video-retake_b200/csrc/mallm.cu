@@ -164,6 +164,7 @@ __device__ __forceinline__ int block_argmax(const float* v, long long stride, in
 // ------------------------------------------------------------------------------------------------ init
 // one CTA per patch: norms, sizes, links, all adjacent similarities
 __global__ void __launch_bounds__(kMlThreads) mallm_init_kernel(MallmParams P) {
+    pdl_enter();
     __shared__ int s_cnt;
     const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) s_cnt = 0;
@@ -211,6 +212,7 @@ __device__ __forceinline__ uint32_t rescale_pair(uint32_t a, float s) {
 
 // soft merge: one CTA per patch, `round` = number of merges already done
 __global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, int round) {
+    pdl_enter();
     __shared__ Best s_best[kMlWarps];
     __shared__ int s_m, s_n, s_cnt;
     const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -320,6 +322,7 @@ __global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, 
 
 // hard variant: frame m is deleted, nothing is rewritten
 __global__ void __launch_bounds__(kMlThreads) mallm_hard_round_kernel(MallmParams P, int round) {
+    pdl_enter();
     __shared__ Best s_best[kMlWarps];
     const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = P.T;
@@ -382,6 +385,7 @@ __device__ __forceinline__ float aten_row_sum_bf16(const float* __restrict__ row
 // one CTA: refresh the mean similarity of the rows rewritten in the round stamped `stamp` (all rows when the row
 // alignment depends on the position, i.e. N % 8 != 0), then the shared argmax
 __global__ void __launch_bounds__(1024) mallm_sync_argmax_kernel(MallmParams P, int stamp) {
+    pdl_enter();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     int* pos = reinterpret_cast<int*>(smem_raw);                 // [T] index of frame i among the survivors
     __shared__ int s_warp_tot[32];
@@ -440,6 +444,7 @@ __global__ void __launch_bounds__(1024) mallm_sync_argmax_kernel(MallmParams P, 
 // one CTA per patch: surviving rows in frame order -> out[pos, p, :], sizes_out[pos, p]
 __global__ void __launch_bounds__(kMlThreads) mallm_emit_kernel(MallmParams P, __nv_bfloat16* __restrict__ out,
                                                                __nv_bfloat16* __restrict__ sizes_out, int t) {
+    pdl_enter();
     extern __shared__ __align__(16) uint8_t smem_raw[];
     int* order = reinterpret_cast<int*>(smem_raw);               // [t]
     __shared__ int s_warp_tot[kMlWarps];
@@ -555,26 +560,23 @@ extern "C" int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T
         cudaError_t e = cudaFuncSetAttribute(mallm_sync_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
         if (e != cudaSuccess) return (int)e;
     }
-    mallm_init_kernel<<<(unsigned)N, kMlThreads, 0, stream>>>(P);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(mallm_init_kernel, (unsigned)N, kMlThreads, 0, stream, P);
     if (sync && t < T) {
-        mallm_sync_argmax_kernel<<<1, 1024, scan_smem, stream>>>(P, 0);
-        RTK_CHECK_LAUNCH();
+        RTK_LAUNCH_PDL(mallm_sync_argmax_kernel, 1, 1024, scan_smem, stream, P, 0);
     }
     for (int r = 0; r < (int)(T - t); ++r) {
-        if (hard) mallm_hard_round_kernel<<<(unsigned)N, kMlThreads, 0, stream>>>(P, r);
-        else mallm_round_kernel<<<(unsigned)N, kMlThreads, 0, stream>>>(P, r);
-        RTK_CHECK_LAUNCH();
+        if (hard) {
+            RTK_LAUNCH_PDL(mallm_hard_round_kernel, (unsigned)N, kMlThreads, 0, stream, P, r);
+        } else {
+            RTK_LAUNCH_PDL(mallm_round_kernel, (unsigned)N, kMlThreads, 0, stream, P, r);
+        }
         if (sync && r + 1 < (int)(T - t)) {
-            mallm_sync_argmax_kernel<<<1, 1024, scan_smem, stream>>>(P, r + 1);
-            RTK_CHECK_LAUNCH();
+            RTK_LAUNCH_PDL(mallm_sync_argmax_kernel, 1, 1024, scan_smem, stream, P, r + 1);
         }
     }
     const size_t emit_smem = (size_t)t * 4;
     cudaError_t e = cudaFuncSetAttribute(mallm_emit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)emit_smem);
     if (e != cudaSuccess) return (int)e;
-    mallm_emit_kernel<<<(unsigned)N, kMlThreads, emit_smem, stream>>>(P, static_cast<__nv_bfloat16*>(out),
-                                                                    hard ? nullptr : static_cast<__nv_bfloat16*>(sizes_out), (int)t);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(mallm_emit_kernel, (unsigned)N, kMlThreads, emit_smem, stream, P, static_cast<__nv_bfloat16*>(out), hard ? nullptr : static_cast<__nv_bfloat16*>(sizes_out), (int)t);
     return 0;
 }

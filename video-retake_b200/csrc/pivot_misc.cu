@@ -2,6 +2,8 @@
 // Replaces retake/longvideo_cache.py:248-259 (B0), :270-277 (B2), :278-306 (B3).
 #include <climits>
 
+#include <stdlib.h>
+
 #include "rtk_common.cuh"
 
 namespace rtk {
@@ -32,6 +34,7 @@ __device__ __forceinline__ int rope_pos_row(const RopeParams& p, int c) {
 __global__ void __launch_bounds__(256)
 pivot_rope_table_kernel(const long long* __restrict__ pos, const float* __restrict__ inv_freq, RopeParams p, float scaling,
                         __nv_bfloat16* __restrict__ cos_t, __nv_bfloat16* __restrict__ sin_t) {
+    pdl_enter();
     const int half = p.D >> 1;
     const long long total = (long long)p.L * p.D;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -48,6 +51,7 @@ pivot_rope_table_kernel(const long long* __restrict__ pos, const float* __restri
 __global__ void __launch_bounds__(256)
 pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ cos_t,
                   const __nv_bfloat16* __restrict__ sin_t, __nv_bfloat16* __restrict__ out, RopeParams p) {
+    pdl_enter();
     const int half = p.D >> 1;
     const int vec_per_row = half >> 3;
     const long long total = (long long)(p.heads + p.heads2) * p.L * vec_per_row;
@@ -187,6 +191,7 @@ __device__ void block_select_top(const uint32_t* keys, int L, int keep, int32_t*
 __global__ void __launch_bounds__(kSelThreads)
 pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int L, const uint8_t* __restrict__ keymask,
                     int keep, int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ score_out) {
+    pdl_enter();
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem);        // [L]
     int* sh = reinterpret_cast<int*>(smem + (size_t)L * 4);    // scratch
@@ -218,6 +223,7 @@ pivot_compact_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* _
                      const int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ k_out,
                      __nv_bfloat16* __restrict__ v_out, const long long* __restrict__ pos,
                      long long* __restrict__ pos_out, CompactParams p) {
+    pdl_enter();
     if (blockIdx.x == gridDim.x - 1) {
         if (!pos) return;
         __shared__ long long smin[32];
@@ -271,6 +277,7 @@ struct CopyJobs {
 
 __global__ void __launch_bounds__(256)
 kv_block_copy_kernel(CopyJobs j) {
+    pdl_enter();
     const int vpr = j.D >> 3;
     const long long total = j.vec_end[j.n - 1];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -287,6 +294,13 @@ kv_block_copy_kernel(CopyJobs j) {
 }
 
 long long g_launches = 0;
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("RTK_NO_PDL");
+        return !(e && e[0] && e[0] != '0');
+    }();
+    return on;
+}
 
 }  // namespace rtk
 
@@ -333,9 +347,7 @@ extern "C" int rtk_pivot_rope(const void* x, int64_t heads, int64_t L, int64_t D
     const long long total = heads * L * (D / 16);
     long long grid = (total + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
-    pivot_rope_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)x, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, (__nv_bfloat16*)out, p);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(pivot_rope_kernel, (unsigned)grid, 256, 0, (cudaStream_t)stream,  (const __nv_bfloat16*)x, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, (__nv_bfloat16*)out, p);
     return 0;
 }
 
@@ -346,9 +358,7 @@ extern "C" int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L,
     const size_t smem = (size_t)L * 4 + 112 * 4;
     cudaError_t e = cudaFuncSetAttribute(pivot_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    pivot_select_kernel<<<1, kSelThreads, smem, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)head_scores, (int)KVH, (int)L, keymask, (int)keep, keep_idx, (__nv_bfloat16*)score_out);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream,  (const __nv_bfloat16*)head_scores, (int)KVH, (int)L, keymask, (int)keep, keep_idx, (__nv_bfloat16*)score_out);
     return 0;
 }
 
@@ -381,10 +391,7 @@ static int compact_kv(const void* k, const void* v, int64_t KVH, int64_t L, int6
     const long long total = KVH * keep * (D / 8);
     long long grid = (total + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
-    pivot_compact_kernel<<<(unsigned)(grid + 1), 256, 0, (cudaStream_t)stream>>>(
-        (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, keep_idx, (__nv_bfloat16*)k_out, (__nv_bfloat16*)v_out,
-        (const long long*)pos, (long long*)pos_out, p);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(pivot_compact_kernel, (unsigned)(grid + 1), 256, 0, (cudaStream_t)stream,  (const __nv_bfloat16*)k, (const __nv_bfloat16*)v, keep_idx, (__nv_bfloat16*)k_out, (__nv_bfloat16*)v_out, (const long long*)pos, (long long*)pos_out, p);
     return 0;
 }
 
@@ -408,9 +415,7 @@ extern "C" int rtk_pivot_rope_tables(const int64_t* pos, int n_pos, int64_t L, i
     if (n_pos == 3 && acc != D) return RTK_E_UNSUPPORTED;
     long long grid = (L * D + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
-    pivot_rope_table_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-        (const long long*)pos, inv_freq, p, attention_scaling, (__nv_bfloat16*)cos_out, (__nv_bfloat16*)sin_out);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(pivot_rope_table_kernel, (unsigned)grid, 256, 0, (cudaStream_t)stream,  (const long long*)pos, inv_freq, p, attention_scaling, (__nv_bfloat16*)cos_out, (__nv_bfloat16*)sin_out);
     return 0;
 }
 
@@ -435,9 +440,7 @@ static int rope_qk_reverse(const void* q, int64_t H, int64_t qsh, int64_t qsl, c
     const long long total = (H + KVH) * L * (D / 16);
     long long grid = (total + 255) / 256;
     if (grid > 148 * 16) grid = 148 * 16;
-    pivot_rope_kernel<<<(unsigned)grid, 256, 0, st>>>((const __nv_bfloat16*)q, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin,
-                                                      (__nv_bfloat16*)qu, p);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(pivot_rope_kernel, (unsigned)grid, 256, 0, st, (const __nv_bfloat16*)q, (const __nv_bfloat16*)cos, (const __nv_bfloat16*)sin, (__nv_bfloat16*)qu, p);
     return 0;
 }
 
@@ -533,7 +536,6 @@ extern "C" int rtk_kv_block_copy(int n_jobs, const void* const* src, void* const
     if (acc == 0) return 0;
     long long grid = (acc + 255) / 256;
     if (grid > 148 * 8) grid = 148 * 8;
-    kv_block_copy_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(j);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(kv_block_copy_kernel, (unsigned)grid, 256, 0, (cudaStream_t)stream, j);
     return 0;
 }

@@ -382,6 +382,7 @@ constexpr int kTileArrivals = RTK_SCORE_GROUPS ? 4 * kChunksPerTile : 8;       /
 template <int PASS>
 __global__ void __launch_bounds__(kScoreThreads2, 1)
 pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map, ScoreParams prm) {
+    pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for the swizzle atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -410,6 +411,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();                                              // everything above overlapped the previous kernel's tail
     const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(smem + ScoreSmem::tmem_ptr);
 
     const int nt = prm.nt;
@@ -642,6 +644,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
 
 // pass 1 epilogue: fold the (at most two) partial row statistics of every query into c_q = m*log2e + log2(l)
 __global__ void pivot_stats_merge_kernel(const float2* __restrict__ ml_part, int H, int L, int Lpad, float* __restrict__ stats) {
+    pdl_enter();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = blockIdx.y;
     if (q >= Lpad) return;
@@ -657,6 +660,7 @@ __global__ void pivot_stats_merge_kernel(const float2* __restrict__ ml_part, int
 // a = bf16(colsum);  head_scores[g] = bf16((sum over the G heads of group g, ATen 4-accumulator order) * f32(1/G))
 __global__ void pivot_head_reduce_kernel(const float* __restrict__ colsum_part, int H, int G, int L, int Lpad,
                                          __nv_bfloat16* __restrict__ head_scores) {
+    pdl_enter();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
     if (k >= L) return;
@@ -755,16 +759,11 @@ extern "C" int rtk_pivot_score(const void* q, int64_t H, int64_t q_stride_h, int
     if (e != cudaSuccess) return (int)e;
     e = cudaFuncSetAttribute(pivot_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    pivot_score_kernel<1><<<grid, kScoreThreads2, smem, st>>>(qm, km, prm);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(pivot_score_kernel<1>, grid, kScoreThreads2, smem, st, qm, km, prm);
     dim3 g1((unsigned)((prm.nt * kTile + 255) / 256), (unsigned)H);
-    pivot_stats_merge_kernel<<<g1, 256, 0, st>>>(prm.ml_part, (int)H, (int)L, prm.nt * kTile, prm.stats);
-    RTK_CHECK_LAUNCH();
-    pivot_score_kernel<2><<<grid, kScoreThreads2, smem, st>>>(qm, km, prm);
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(pivot_stats_merge_kernel, g1, 256, 0, st, prm.ml_part, (int)H, (int)L, prm.nt * kTile, prm.stats);
+    RTK_LAUNCH_PDL(pivot_score_kernel<2>, grid, kScoreThreads2, smem, st, qm, km, prm);
     dim3 g2((unsigned)((L + 255) / 256), (unsigned)KVH);
-    pivot_head_reduce_kernel<<<g2, 256, 0, st>>>(prm.colsum_part, (int)H, prm.G, (int)L, prm.nt * kTile,
-                                                 reinterpret_cast<__nv_bfloat16*>(head_scores));
-    RTK_CHECK_LAUNCH();
+    RTK_LAUNCH_PDL(pivot_head_reduce_kernel, g2, 256, 0, st, prm.colsum_part, (int)H, prm.G, (int)L, prm.nt * kTile, reinterpret_cast<__nv_bfloat16*>(head_scores));
     return 0;
 }

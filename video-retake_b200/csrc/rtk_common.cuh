@@ -21,6 +21,43 @@ extern long long g_launches;  // host-side launch counter (rtk_launch_count)
 
 constexpr int kWarp = 32;
 
+// ------------------------------------------------------------------------ programmatic dependent launch (PDL)
+// The operators are chains of small dependent kernels on one stream.  Launched with the programmatic-stream-
+// serialization attribute a kernel may become resident while its predecessor is still running; every kernel
+// therefore starts with pdl_enter(): it lets ITS successor be scheduled (launch_dependents) and then blocks until
+// the predecessor grid has completed and its writes are visible (wait).  For a normal launch both are no-ops.
+// RTK_NO_PDL=1 in the environment turns the attribute off (A/B and debugging).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+    pdl_trigger();
+    pdl_wait();
+}
+
+bool pdl_enabled();  // pivot_misc.cu
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                     Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#define RTK_LAUNCH_PDL(kern, grid, block, smem, st, ...)                                                  \
+    do {                                                                                                  \
+        ++::rtk::g_launches;                                                                              \
+        cudaError_t le__ = ::rtk::launch_pdl(kern, dim3(grid), dim3(block), (size_t)(smem), st, __VA_ARGS__); \
+        if (le__ != cudaSuccess) return (int)le__;                                                        \
+    } while (0)
+
 // ---------------------------------------------------------------------------------------------- bf16 bits
 // A bf16 value widened to fp32 is its 16 bits in the upper half of the word.
 __device__ __forceinline__ float bf16lo_to_f32(uint32_t packed) { return __uint_as_float(packed << 16); }
