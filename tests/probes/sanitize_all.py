@@ -15,6 +15,13 @@ for (T, N, C) in ((9, 5, 256), (7, 33, 1152), (5, 3, 3584)):
         for t in (T, max(1, T // 2), 1):
             out, mask, idx = vc.memory_bank_compress_keyframe(x[None], t, 3, sync=sync, return_indices=True)
     d = vc.dpselect_distance(x[1:], halo=True)
+    for sync in (False, True):                                   # MA-LLM compressors, soft and hard
+        for hard in (False, True):
+            for t in (T - 1, max(1, T // 2), 1):
+                vc.mallm_compress(x[None], t, sync=sync, hard=hard)
+xm = scene_video(g, 11, 137, 256, dup_every=3).to(torch.bfloat16).cuda()      # N % 8 != 0, N >= 128: position-dependent mean
+for hard in (False, True):
+    vc.mallm_compress(xm[None], 4, sync=True, hard=hard)
 for (H, KVH, L, D) in ((4, 2, 130, 64), (28, 4, 200, 128), (8, 8, 1, 128)):
     cfg = types.SimpleNamespace(hidden_size=H * D, num_hidden_layers=2, num_attention_heads=H, num_key_value_heads=KVH)
     for reforge in (False, True):
