@@ -47,6 +47,77 @@ pivot_rope_table_kernel(const long long* __restrict__ pos, const float* __restri
     }
 }
 
+// channel c of the lower half (xa, tables cosa/sina) and its partner c + D/2 (xb, cosb/sinb), every product and sum
+// rounded to bf16 like the reference's op-by-op bf16 expression (longvideo_cache.py:36-83)
+__device__ __forceinline__ void rope_rotate_pair(float xa, float xb, float cosa, float sina, float cosb, float sinb, int forward,
+                                                 float inv_scale2, __nv_bfloat16& oa, __nv_bfloat16& ob) {
+    // rotate_half: lower half pairs with -x[c + D/2], upper half with +x[c - D/2]
+    const float ta = round_bf16(xa * cosa), ra = round_bf16(-xb * sina);
+    const float tb = round_bf16(xb * cosb), rb = round_bf16(xa * sinb);
+    float ya, yb;
+    if (forward) {
+        ya = ta + ra;
+        yb = tb + rb;
+    } else {
+        ya = round_bf16(ta - ra) * inv_scale2;
+        yb = round_bf16(tb - rb) * inv_scale2;
+    }
+    oa = __float2bfloat16_rn(ya);
+    ob = __float2bfloat16_rn(yb);
+}
+
+// cos/sin of channel c at the positions pv[0..n_pos) of one token, as the HF rotary module computes them
+__device__ __forceinline__ void rope_table_entry(const RopeParams& p, const float* __restrict__ inv_freq, const long long* pv,
+                                                 int c, float scaling, float& co, float& si) {
+    const int half = p.D >> 1;
+    const float ang = inv_freq[c < half ? c : c - half] * (float)pv[rope_pos_row(p, c)];
+    co = __bfloat162float(__float2bfloat16_rn(cosf(ang) * scaling));
+    si = __bfloat162float(__float2bfloat16_rn(sinf(ang) * scaling));
+}
+
+// Reverse rotation of q and k with the tables computed in place (fast path: the rotary module has a static inv_freq):
+// one CTA per token, D threads build the token's cos/sin row in shared memory, then every thread rotates one
+// (head, 8+8 channel) slice of q or k.  Replaces pivot_rope_table_kernel + pivot_rope_kernel of the slow path.
+__global__ void __launch_bounds__(256)
+pivot_unrope_qk_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ pos, const float* __restrict__ inv_freq,
+                       float scaling, __nv_bfloat16* __restrict__ out, RopeParams p) {
+    pdl_enter();
+    __shared__ float s_cos[256], s_sin[256];
+    const int half = p.D >> 1;
+    const int vec_per_row = half >> 3;
+    const int ntask = (p.heads + p.heads2) * vec_per_row;
+    for (int l = blockIdx.x; l < p.L; l += gridDim.x) {
+        if (threadIdx.x < p.D) {
+            long long pv[3] = {0, 0, 0};
+            for (int r = 0; r < p.n_pos; ++r) pv[r] = pos[(size_t)r * p.L + l];
+            rope_table_entry(p, inv_freq, pv, threadIdx.x, scaling, s_cos[threadIdx.x], s_sin[threadIdx.x]);
+        }
+        __syncthreads();
+        for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
+            const int v = task % vec_per_row, h = task / vec_per_row;
+            const int c0 = v * 8;
+            const bool second = h >= p.heads;
+            const __nv_bfloat16* src = second ? p.x2 + (h - p.heads) * p.stride_h2 + l * p.stride_l2 : x + h * p.stride_h + l * p.stride_l;
+            __nv_bfloat16* dst = second ? p.out2 + (h - p.heads) * p.out_stride_h2 + l * p.out_stride_l2
+                                        : out + h * p.out_stride_h + l * p.out_stride_l;
+            uint4 lo4 = *reinterpret_cast<const uint4*>(src + c0);
+            uint4 hi4 = *reinterpret_cast<const uint4*>(src + c0 + half);
+            const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(&lo4);
+            const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(&hi4);
+            uint4 ol4, oh4;
+            __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(&ol4);
+            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&oh4);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                rope_rotate_pair(__bfloat162float(xl[e]), __bfloat162float(xh[e]), s_cos[c0 + e], s_sin[c0 + e], s_cos[c0 + half + e],
+                                 s_sin[c0 + half + e], 0, p.inv_scale2, ol[e], oh[e]);
+            *reinterpret_cast<uint4*>(dst + c0) = ol4;
+            *reinterpret_cast<uint4*>(dst + c0 + half) = oh4;
+        }
+        __syncthreads();
+    }
+}
+
 // one thread: 8 channels of the lower half and the 8 partner channels of the upper half of one (head, token)
 __global__ void __launch_bounds__(256)
 pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ cos_t,
@@ -96,24 +167,9 @@ pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
             }
         }
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float xa = __bfloat162float(xl[e]), xb = __bfloat162float(xh[e]);
-            const float cosa = __bfloat162float(cav[e]), sina = __bfloat162float(sav[e]);
-            const float cosb = __bfloat162float(cbv[e]), sinb = __bfloat162float(sbv[e]);
-            // rotate_half: lower half pairs with -x[c + D/2], upper half with +x[c - D/2]
-            const float ta = round_bf16(xa * cosa), ra = round_bf16(-xb * sina);
-            const float tb = round_bf16(xb * cosb), rb = round_bf16(xa * sinb);
-            float ya, yb;
-            if (p.forward) {
-                ya = ta + ra;
-                yb = tb + rb;
-            } else {
-                ya = round_bf16(ta - ra) * p.inv_scale2;
-                yb = round_bf16(tb - rb) * p.inv_scale2;
-            }
-            ol[e] = __float2bfloat16_rn(ya);
-            oh[e] = __float2bfloat16_rn(yb);
-        }
+        for (int e = 0; e < 8; ++e)
+            rope_rotate_pair(__bfloat162float(xl[e]), __bfloat162float(xh[e]), __bfloat162float(cav[e]), __bfloat162float(sav[e]),
+                             __bfloat162float(cbv[e]), __bfloat162float(sbv[e]), p.forward, p.inv_scale2, ol[e], oh[e]);
         *reinterpret_cast<uint4*>(dst + c0) = ol4;
         *reinterpret_cast<uint4*>(dst + c0 + half) = oh4;
     }
@@ -190,7 +246,8 @@ __device__ void block_select_top(const uint32_t* keys, int L, int keep, int32_t*
 
 __global__ void __launch_bounds__(kSelThreads)
 pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int L, const uint8_t* __restrict__ keymask,
-                    int keep, int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ score_out) {
+                    int keep, int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ score_out,
+                    const long long* __restrict__ tpos, long long* __restrict__ tmin_out) {
     pdl_enter();
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem);        // [L]
@@ -207,6 +264,21 @@ pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int 
     }
     __syncthreads();
     block_select_top(keys, L, keep, keep_idx, sh, 16);        // bf16 scores: the low 16 key bits are zero
+    if (tmin_out) {
+        // smallest temporal position among the kept tokens (longvideo_cache.py:291) for the fused compaction
+        __syncthreads();
+        long long* smin = reinterpret_cast<long long*>((reinterpret_cast<uintptr_t>(sh) + 7) & ~(uintptr_t)7);
+        long long mn = LLONG_MAX;
+        for (int j = threadIdx.x; j < keep; j += blockDim.x) mn = min(mn, tpos[keep_idx[j]]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        if ((threadIdx.x & 31) == 0) smin[threadIdx.x >> 5] = mn;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w) mn = min(mn, smin[w]);
+            *tmin_out = mn;
+        }
+    }
 }
 
 // ======================================================================================= B3: compaction
@@ -260,6 +332,66 @@ pivot_compact_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* _
         const size_t dof = (size_t)h * p.out_stride_h + (size_t)j * p.D + (size_t)c * 8;
         if (k) *reinterpret_cast<uint4*>(k_out + dof) = __ldg(reinterpret_cast<const uint4*>(k + so));
         if (v) *reinterpret_cast<uint4*>(v_out + dof) = __ldg(reinterpret_cast<const uint4*>(v + sv));
+    }
+}
+
+// Fused tail of an update (fast path): one CTA per kept token gathers its K and V rows of every KV head, writes its
+// (re-indexed) position ids and - when re-forging - rotates K to the new position with the cos/sin row built in place.
+// Replaces pivot_compact_kernel + pivot_rope_table_kernel + pivot_rope_kernel (longvideo_cache.py:278-306).
+__global__ void __launch_bounds__(128)
+pivot_compact_rope_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                          const int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ k_out,
+                          __nv_bfloat16* __restrict__ v_out, const long long* __restrict__ pos, long long* __restrict__ pos_out,
+                          const long long* __restrict__ tmin, const float* __restrict__ inv_freq, float scaling, CompactParams p,
+                          RopeParams rp, int rotate) {
+    pdl_enter();
+    __shared__ float s_cos[256], s_sin[256];
+    __shared__ long long s_pos[3];
+    const int j = blockIdx.x, tid = threadIdx.x;
+    const int src_row = keep_idx[j];
+    if (pos && tid < p.n_pos) {
+        long long pv = pos[(size_t)tid * p.L + src_row];
+        if (p.reforge && tid == 0) {
+            // m + ((p - m) * ratio).long(): int64 tensor times python float -> fp32 product, truncation toward zero
+            const long long mn = *tmin;
+            pv = mn + (long long)((float)(pv - mn) * p.ratio);
+        }
+        pos_out[(size_t)tid * p.keep + j] = pv;
+        s_pos[tid] = pv;
+    }
+    const int vec_per_row = p.D >> 3;
+    // V rows (and K rows when nothing is rotated): plain 16-byte copies
+    for (int t = tid; t < p.KVH * vec_per_row; t += blockDim.x) {
+        const int c = t % vec_per_row, h = t / vec_per_row;
+        const size_t dof = (size_t)h * p.out_stride_h + (size_t)j * p.D + (size_t)c * 8;
+        *reinterpret_cast<uint4*>(v_out + dof) =
+            __ldg(reinterpret_cast<const uint4*>(v + (size_t)h * p.v_stride_h + (size_t)src_row * p.v_stride_l + (size_t)c * 8));
+        if (!rotate)
+            *reinterpret_cast<uint4*>(k_out + dof) =
+                __ldg(reinterpret_cast<const uint4*>(k + (size_t)h * p.stride_h + (size_t)src_row * p.stride_l + (size_t)c * 8));
+    }
+    if (!rotate) return;
+    __syncthreads();
+    if (tid < p.D) rope_table_entry(rp, inv_freq, s_pos, tid, scaling, s_cos[tid], s_sin[tid]);
+    __syncthreads();
+    const int half = p.D >> 1, hv = half >> 3;
+    for (int t = tid; t < p.KVH * hv; t += blockDim.x) {
+        const int c0 = (t % hv) * 8, h = t / hv;
+        const __nv_bfloat16* src = k + (size_t)h * p.stride_h + (size_t)src_row * p.stride_l;
+        __nv_bfloat16* dst = k_out + (size_t)h * p.out_stride_h + (size_t)j * p.D;
+        uint4 lo4 = *reinterpret_cast<const uint4*>(src + c0);
+        uint4 hi4 = *reinterpret_cast<const uint4*>(src + c0 + half);
+        const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(&lo4);
+        const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(&hi4);
+        uint4 ol4, oh4;
+        __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(&ol4);
+        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&oh4);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            rope_rotate_pair(__bfloat162float(xl[e]), __bfloat162float(xh[e]), s_cos[c0 + e], s_sin[c0 + e], s_cos[c0 + half + e],
+                             s_sin[c0 + half + e], 1, 1.0f, ol[e], oh[e]);
+        *reinterpret_cast<uint4*>(dst + c0) = ol4;
+        *reinterpret_cast<uint4*>(dst + c0 + half) = oh4;
     }
 }
 
@@ -358,7 +490,8 @@ extern "C" int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L,
     const size_t smem = (size_t)L * 4 + 112 * 4;
     cudaError_t e = cudaFuncSetAttribute(pivot_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream,  (const __nv_bfloat16*)head_scores, (int)KVH, (int)L, keymask, (int)keep, keep_idx, (__nv_bfloat16*)score_out);
+    RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream, (const __nv_bfloat16*)head_scores, (int)KVH,
+                   (int)L, keymask, (int)keep, keep_idx, (__nv_bfloat16*)score_out, (const long long*)nullptr, (long long*)nullptr);
     return 0;
 }
 
@@ -449,7 +582,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 extern "C" size_t rtk_pivot_update_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D) {
     if (H < 1 || KVH < 1 || L < 1 || D < 1) return 0;
     return align256(rtk_pivot_score_workspace_bytes(H, L)) + align256((size_t)H * L * D * 2) + align256((size_t)KVH * L * D * 2) +
-           4 * align256((size_t)L * D * 2);
+           4 * align256((size_t)L * D * 2) + 256;
 }
 
 extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
@@ -465,7 +598,9 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
     void* cos1 = ws;                    ws += align256((size_t)L * D * 2);
     void* sin1 = ws;                    ws += align256((size_t)L * D * 2);
     void* cos2 = ws;                    ws += align256((size_t)L * D * 2);
-    void* sin2 = ws;
+    void* sin2 = ws;                    ws += align256((size_t)L * D * 2);
+    long long* tmin = (long long*)ws;   // smallest kept temporal position (select -> fused compaction)
+    (void)cos2; (void)sin2;
     const void* q = a->q;
     const void* k = a->k;
     int64_t qsh = a->q_stride_h, qsl = a->q_stride_l, ksh = a->k_stride_h, ksl = a->k_stride_l;
@@ -477,15 +612,28 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
         int n_pos_tab = a->n_pos;
         const int32_t* sec = a->n_pos == 3 ? a->mrope_section : nullptr;
         if (fused_tables) {
-            rc = rtk_pivot_rope_tables(a->pos, a->n_pos, L, D, a->inv_freq, sec, a->attention_scaling, cos1, sin1, stream);
+            // tables computed inside the rotation kernel: one launch for q and k
+            if ((((uintptr_t)q | (uintptr_t)k) & 15u) != 0 || (qsh | qsl | ksh | ksl) % 8 != 0 || D % 16 != 0 || D > 256) return RTK_E_ALIGN;
+            RopeParams p;
+            p.heads = (int)H; p.L = (int)L; p.D = (int)D; p.n_pos = a->n_pos; p.forward = 0;
+            p.stride_h = qsh; p.stride_l = qsl; p.out_stride_h = L * D; p.out_stride_l = D;
+            p.heads2 = (int)KVH; p.x2 = (const __nv_bfloat16*)k; p.out2 = (__nv_bfloat16*)ku;
+            p.stride_h2 = ksh; p.stride_l2 = ksl; p.out_stride_h2 = L * D; p.out_stride_l2 = D;
+            p.inv_scale2 = a->inv_scale2;
+            int acc = 0;
+            for (int i = 0; i < 6; ++i) {
+                acc += sec ? sec[i % 3] : 0;
+                p.bound[i] = acc;
+            }
+            if (sec && acc != D) return RTK_E_UNSUPPORTED;
+            RTK_LAUNCH_PDL(pivot_unrope_qk_kernel, (unsigned)L, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)q,
+                           (const long long*)a->pos, a->inv_freq, a->attention_scaling, (__nv_bfloat16*)qu, p);
+        } else {
+            if (!c || !s) return RTK_E_BADARG;
+            rc = rope_qk_reverse(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, c, s, n_pos_tab, sec, a->inv_scale2, qu, ku,
+                                 (cudaStream_t)stream);
             if (rc) return rc;
-            c = cos1; s = sin1; n_pos_tab = 1; sec = nullptr;
-        } else if (!c || !s) {
-            return RTK_E_BADARG;
         }
-        rc = rope_qk_reverse(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, c, s, n_pos_tab, sec, a->inv_scale2, qu, ku,
-                             (cudaStream_t)stream);
-        if (rc) return rc;
         q = qu; k = ku; qsh = ksh = L * D; qsl = ksl = D;
     }
     if (a->ev_score_begin) cudaEventRecord((cudaEvent_t)a->ev_score_begin, (cudaStream_t)stream);
@@ -493,19 +641,38 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
     if (rc) return rc;
     if (a->ev_score_end) cudaEventRecord((cudaEvent_t)a->ev_score_end, (cudaStream_t)stream);
     if (a->skip_select) return 0;
-    rc = rtk_pivot_select(a->head_scores, KVH, L, a->keymask, a->keep, a->keep_idx, nullptr, stream);
-    if (rc) return rc;
-    // K (possibly the un-rotated copy) and V (caller's strides) + positions in one launch
-    rc = compact_kv(k, a->v, KVH, L, D, ksh, ksl, a->v_stride_h, a->v_stride_l, a->keep_idx, a->keep, a->k_out, a->v_out,
-                    a->out_stride_h, a->pos, a->pos ? a->n_pos : 0, a->pos_out, a->reforge, stream);
-    if (rc) return rc;
-    if (fused_tables) {
-        const int32_t* sec = a->n_pos == 3 ? a->mrope_section : nullptr;
-        rc = rtk_pivot_rope_tables(a->pos_out, a->n_pos, a->keep, D, a->inv_freq, sec, a->attention_scaling, cos2, sin2, stream);
-        if (rc) return rc;
-        rc = rtk_pivot_rope(a->k_out, KVH, a->keep, D, a->out_stride_h, D, cos2, sin2, 1, nullptr, 1.0f, 1, a->k_out,
-                            a->out_stride_h, D, stream);
-        if (rc) return rc;
+    {
+        if (a->keep < 1 || a->keep > L) return RTK_E_BADARG;
+        if (L > 16384) return RTK_E_UNSUPPORTED;
+        const size_t smem = (size_t)L * 4 + 112 * 4;
+        cudaError_t e = cudaFuncSetAttribute(pivot_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream, (const __nv_bfloat16*)a->head_scores,
+                       (int)KVH, (int)L, a->keymask, (int)a->keep, a->keep_idx, (__nv_bfloat16*)nullptr,
+                       (const long long*)(a->reforge ? a->pos : nullptr), a->reforge ? tmin : (long long*)nullptr);
+    }
+    // K (possibly the un-rotated copy), V (caller's strides), positions and - on the fast path - the forward rotation
+    // at the re-indexed positions: one launch, one CTA per kept token
+    {
+        if ((((uintptr_t)k | (uintptr_t)a->v | (uintptr_t)a->k_out | (uintptr_t)a->v_out) & 15u) != 0) return RTK_E_ALIGN;
+        if ((ksh | ksl | a->v_stride_h | a->v_stride_l | a->out_stride_h) % 8 != 0 || D % 16 != 0 || D > 256) return RTK_E_ALIGN;
+        if (a->pos && (!a->pos_out || a->n_pos < 1 || a->n_pos > 3)) return RTK_E_BADARG;
+        CompactParams p;
+        p.KVH = (int)KVH; p.L = (int)L; p.D = (int)D; p.keep = (int)a->keep; p.n_pos = a->pos ? a->n_pos : 0; p.reforge = a->reforge;
+        p.stride_h = ksh; p.stride_l = ksl; p.out_stride_h = a->out_stride_h;
+        p.v_stride_h = a->v_stride_h; p.v_stride_l = a->v_stride_l;
+        p.ratio = (float)((double)a->keep / (double)L);
+        RopeParams rp = {};
+        rp.D = (int)D; rp.n_pos = a->n_pos; rp.L = (int)a->keep;
+        int acc = 0;
+        for (int i = 0; i < 6; ++i) {
+            acc += (a->n_pos == 3) ? a->mrope_section[i % 3] : 0;
+            rp.bound[i] = acc;
+        }
+        RTK_LAUNCH_PDL(pivot_compact_rope_kernel, (unsigned)a->keep, 128, 0, (cudaStream_t)stream, (const __nv_bfloat16*)k,
+                       (const __nv_bfloat16*)a->v, (const int32_t*)a->keep_idx, (__nv_bfloat16*)a->k_out, (__nv_bfloat16*)a->v_out,
+                       (const long long*)a->pos, (long long*)a->pos_out, (const long long*)tmin, a->inv_freq, a->attention_scaling, p,
+                       rp, fused_tables ? 1 : 0);
     }
     return 0;
 }
