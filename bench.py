@@ -403,9 +403,12 @@ def main():
                 "ms_per_call": score_ms, "calls_timed": len(timer.pairs),
                 # dram__bytes_read.sum + dram__bytes_write.sum of both launches, profiles/r1_ncu_score_summary.txt (L=4096)
                 "traffic": 67.6e6 if s.L == 4096 else None,
-                "note": ("algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it twice and is bounded by the "
-                         "softmax warps' instruction stream (math-only 0.349 ms, TMEM-only floor 0.238 ms), not the tensor pipe "
-                         "(DESIGN.md section 5)")}
+                # an exact two-pass softmax needs 2*H*L^2 fp32 ex2; B200 issues 16 MUFU per clock and SM
+                "xu_floor_ms": 2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3,
+                "frac_of_xu_floor": (2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3) / score_ms if score_ms > 0 else 0.0,
+                "note": ("algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it twice and is bounded by "
+                         "MUFU.EX2 throughput and the softmax warps' instruction stream (XU pipe 73-76 % busy; xu_floor_ms = "
+                         "2*H*L^2 exps at 16/clk/SM, 1.9 GHz), not by the tensor pipe (36 % busy) - DESIGN.md section 5")}
     dps_ms = sum(a.elapsed_time(b) for a, b in timer.dpselect) / max(1, len(timer.dpselect))
     hbm = peaks.get("hbm_gbs", 6650.0)
     dps_bytes = 2.0 * s.T * s.N * s.C + 4.0 * s.T * s.N + 4.0 * s.t * s.N * s.C
