@@ -10,7 +10,8 @@
 //     of frames m and next(m), and the replay of the reference's `x = rd(rd(x * size) / size)` on the rows for
 //     which that map is not yet at a fixed point (it is idempotent after one or two applications, so the "dirty"
 //     list holds the rows changed in the previous round only), then the similarities next to changed rows;
-//   * sync mode shares one argmax over the bf16 mean of the similarities across patches (second kernel per round).
+//   * patch-local mode runs all rounds of a patch column inside one CTA of one launch; sync mode shares one argmax
+//     over the bf16 mean of the similarities across patches (one round kernel + one argmax kernel per round).
 //
 // Arithmetic is the reference's, bit for bit (bf16 bank): rd() = round to nearest even to bf16 after EVERY op,
 // true fp32 division, sizes kept in bf16; cosine similarity as in dpselect.cu (ATen reduction orders: 4-element
@@ -210,16 +211,13 @@ __device__ __forceinline__ uint32_t rescale_pair(uint32_t a, float s) {
     return pack_bf16x2_rn(lo, hi);
 }
 
-// soft merge: one CTA per patch, `round` = number of merges already done
-__global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, int round) {
-    pdl_enter();
-    __shared__ Best s_best[kMlWarps];
-    __shared__ int s_m, s_n, s_cnt;
-    const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+// soft merge of frames m and next(m) of patch p by the whole CTA; `round` = number of merges already done;
+// simv[i * sstride] is the patch's similarity column (global state, or the shared-memory copy of the persistent loop)
+__device__ __forceinline__ void mallm_soft_round(const MallmParams& P, int p, int round, int m, float* simv, long long sstride) {
+    __shared__ int s_n, s_cnt;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T = P.T, C = P.C;
-    const int m = P.sync ? P.merge_at[0] : block_argmax(P.sim + (size_t)p * P.sp, P.si, T, s_best);
     if (threadIdx.x == 0) {
-        s_m = m;
         s_n = P.next[at(P, m, p)];
         s_cnt = 0;
     }
@@ -298,7 +296,7 @@ __global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, 
         P.next[at(P, m, p)] = nx;
         if (nx < T) P.prev[at(P, nx, p)] = m;
         P.alive[at(P, n, p)] = 0;
-        P.sim[at(P, n, p)] = -INFINITY;
+        simv[(size_t)n * sstride] = -INFINITY;
         if (P.sync && p == 0) P.touched[n] = round + 1;
         P.n_dirty[(size_t)((round + 1) & 1) * P.N + p] = s_cnt;
     }
@@ -314,35 +312,59 @@ __global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, 
         float s = -INFINITY;
         if (b < T) s = warp_pair_sim(row_ptr(P, a, p), P.nrm[at(P, a, p)], row_ptr(P, b, p), P.nrm[at(P, b, p)], C, lane);
         if (lane == 0) {
-            P.sim[at(P, a, p)] = s;
+            simv[(size_t)a * sstride] = s;
             if (P.sync) P.touched[a] = round + 1;
         }
     }
 }
 
-// hard variant: frame m is deleted, nothing is rewritten
-__global__ void __launch_bounds__(kMlThreads) mallm_hard_round_kernel(MallmParams P, int round) {
-    pdl_enter();
-    __shared__ Best s_best[kMlWarps];
-    const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T = P.T;
-    const int m = P.sync ? P.merge_at[0] : block_argmax(P.sim + (size_t)p * P.sp, P.si, T, s_best);
+// hard variant: frame m is deleted, nothing is rewritten (one warp's work)
+__device__ __forceinline__ void mallm_hard_round(const MallmParams& P, int p, int round, int m, float* simv, long long sstride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (warp != 0) return;
     const int pm = P.prev[at(P, m, p)], n = P.next[at(P, m, p)];
     float s = 0.f;
     if (pm >= 0) s = warp_pair_sim(row_ptr(P, pm, p), P.nrm[at(P, pm, p)], row_ptr(P, n, p), P.nrm[at(P, n, p)], P.C, lane);
     if (lane == 0) {
         P.alive[at(P, m, p)] = 0;
-        P.sim[at(P, m, p)] = -INFINITY;
+        simv[(size_t)m * sstride] = -INFINITY;
         P.prev[at(P, n, p)] = pm;
         if (pm >= 0) {
             P.next[at(P, pm, p)] = n;
-            P.sim[at(P, pm, p)] = s;
+            simv[(size_t)pm * sstride] = s;
         }
         if (P.sync && p == 0) {
             P.touched[m] = round + 1;
             if (pm >= 0) P.touched[pm] = round + 1;
         }
+    }
+}
+
+// one round per launch (sync mode: the shared argmax comes from mallm_sync_argmax_kernel of the previous launch)
+__global__ void __launch_bounds__(kMlThreads) mallm_round_kernel(MallmParams P, int round) {
+    pdl_enter();
+    __shared__ Best s_best[kMlWarps];
+    const int p = blockIdx.x;
+    float* simv = P.sim + (size_t)p * P.sp;
+    const int m = P.sync ? P.merge_at[0] : block_argmax(simv, P.si, P.T, s_best);
+    if (P.hard) mallm_hard_round(P, p, round, m, simv, P.si);
+    else mallm_soft_round(P, p, round, m, simv, P.si);
+}
+
+// patch-local mode: ALL rounds of one patch column in one CTA, the similarity column lives in shared memory
+__global__ void __launch_bounds__(kMlThreads) mallm_rounds_kernel(MallmParams P, int rounds) {
+    pdl_enter();
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    float* sim_s = reinterpret_cast<float*>(smem_raw);           // [T]
+    __shared__ Best s_best[kMlWarps];
+    const int p = blockIdx.x;
+    for (int i = threadIdx.x; i < P.T; i += blockDim.x) sim_s[i] = P.sim[at(P, i, p)];
+    __syncthreads();
+    for (int r = 0; r < rounds; ++r) {
+        const int m = block_argmax(sim_s, 1, P.T, s_best);
+        if (P.hard) mallm_hard_round(P, p, r, m, sim_s, 1);
+        else mallm_soft_round(P, p, r, m, sim_s, 1);
+        __syncthreads();
     }
 }
 
@@ -564,14 +586,17 @@ extern "C" int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T
     if (sync && t < T) {
         RTK_LAUNCH_PDL(mallm_sync_argmax_kernel, 1, 1024, scan_smem, stream, P, 0);
     }
-    for (int r = 0; r < (int)(T - t); ++r) {
-        if (hard) {
-            RTK_LAUNCH_PDL(mallm_hard_round_kernel, (unsigned)N, kMlThreads, 0, stream, P, r);
-        } else {
-            RTK_LAUNCH_PDL(mallm_round_kernel, (unsigned)N, kMlThreads, 0, stream, P, r);
+    const int rounds = (int)(T - t);
+    if (!sync) {
+        if (rounds > 0) {
+            RTK_LAUNCH_PDL(mallm_rounds_kernel, (unsigned)N, kMlThreads, scan_smem, stream, P, rounds);
         }
-        if (sync && r + 1 < (int)(T - t)) {
-            RTK_LAUNCH_PDL(mallm_sync_argmax_kernel, 1, 1024, scan_smem, stream, P, r + 1);
+    } else {
+        for (int r = 0; r < rounds; ++r) {
+            RTK_LAUNCH_PDL(mallm_round_kernel, (unsigned)N, kMlThreads, 0, stream, P, r);
+            if (r + 1 < rounds) {
+                RTK_LAUNCH_PDL(mallm_sync_argmax_kernel, 1, 1024, scan_smem, stream, P, r + 1);
+            }
         }
     }
     const size_t emit_smem = (size_t)t * 4;
