@@ -382,7 +382,7 @@ constexpr int kTileArrivals = RTK_SCORE_GROUPS ? 4 * kChunksPerTile : 8;       /
 template <int PASS>
 __global__ void __launch_bounds__(kScoreThreads2, 1)
 pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map, ScoreParams prm) {
-    pdl_trigger();
+    if (RTK_PDL_EARLY_SCORE) pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for the swizzle atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;

@@ -29,8 +29,14 @@ constexpr int kWarp = 32;
 // RTK_NO_PDL=1 in the environment turns the attribute off (A/B and debugging).
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifndef RTK_PDL_EARLY_SMALL
+#define RTK_PDL_EARLY_SMALL 1   // small kernels of the PivotKV / MA-LLM chains let their successor in right away
+#endif
+#ifndef RTK_PDL_EARLY_SCORE
+#define RTK_PDL_EARLY_SCORE 1
+#endif
 __device__ __forceinline__ void pdl_enter() {
-    pdl_trigger();
+    if (RTK_PDL_EARLY_SMALL) pdl_trigger();
     pdl_wait();
 }
 
