@@ -51,7 +51,7 @@ struct RowCursor {
 template <int K4>
 __global__ void __launch_bounds__(kDisThreads, (K4 <= 16) ? 2 : 1)
 dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis, int T, int N, int C, int R,
-                    int n_items, int stages, int halo) {
+                    int n_items, int stages, int halo, DisAux aux) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row_bytes = (uint32_t)C * 2u;
@@ -112,6 +112,7 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
 
         float nrm = round_bf16(__fsqrt_rn(ss));
         nrm = fmaxf(nrm, eps);
+        if (aux.nrm && lane == 0) aux.nrm[(size_t)cons.f * aux.si + (size_t)cons.p * aux.sp] = nrm;
         const float rcp = __frcp_rn(nrm);
 #pragma unroll
         for (int k = 0; k < K4; ++k) {
@@ -146,8 +147,11 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
             v += __shfl_down_sync(0xffffffffu, v, 8);        // offset 4
             v += __shfl_down_sync(0xffffffffu, v, 4);        // offset 2
             v += __shfl_down_sync(0xffffffffu, v, 2);        // offset 1  -> 8-lane 0 == physical lane 1
-            if (lane == 1) dis[(size_t)(cons.f - halo) * N + cons.p] = 1.0f - round_bf16(v);
-        } else if (cons.f == 0 && !halo) {
+            if (lane == 1) {
+                if (aux.sim) aux.sim[(size_t)(cons.f - 1) * aux.si + (size_t)cons.p * aux.sp] = round_bf16(v);   // MA-LLM state
+                else dis[(size_t)(cons.f - halo) * N + cons.p] = 1.0f - round_bf16(v);
+            }
+        } else if (cons.f == 0 && !halo && !aux.sim) {
             if (lane == 0) dis[cons.p] = 1.0f;
         }
         ++consumed;
@@ -167,7 +171,7 @@ __global__ void fill_f32_kernel(float* p, int n, float v) {
 }
 
 template <int K4>
-static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, cudaStream_t st) {
+static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, cudaStream_t st, DisAux aux = DisAux{nullptr, nullptr, 0, 0}) {
     int dev = 0, sms = 0, smem_max = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -193,7 +197,7 @@ static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, 
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kDisThreads, smem, st>>>((const __nv_bfloat16*)x, dis, T, N, C, (int)R, (int)n_items,
-                                                     stages, halo);
+                                                     stages, halo, aux);
     RTK_CHECK_LAUNCH();
     return 0;
 }
@@ -413,6 +417,21 @@ gather_rows_kernel(const uint4* __restrict__ x, const long long* __restrict__ sr
         }
         for (; v < nvec; v += 32) dst[v] = __ldg(src + v);
     }
+}
+
+// adjacent-frame similarities (bf16-valued) and clamped row norms into strided state arrays: the first pass of the
+// MA-LLM compressors (mallm.cu) on the streaming kernel above
+int dpselect_sim_nrm(const void* x, int64_t T, int64_t N, int64_t C, DisAux aux, cudaStream_t st) {
+    if (T < 2) return RTK_E_BADARG;
+    const int k4 = (int)((C / 4 + 31) / 32);
+    if (k4 <= 2) return launch_dis<2>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 4) return launch_dis<4>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 9) return launch_dis<9>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 16) return launch_dis<16>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 28) return launch_dis<28>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 32) return launch_dis<32>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 48) return launch_dis<48>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    return launch_dis<64>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
 }
 
 }  // namespace rtk

@@ -68,7 +68,7 @@ __device__ __forceinline__ float warp_tree(float v, int lane) {
 // Rows live in HBM / L2 and every loop below is a chain of dependent round trips unless the loads are issued in
 // batches: kBatch independent vector loads per lane are in flight before the first one is consumed.  The order in
 // which values enter the accumulators is unchanged (ascending vector index per lane).
-constexpr int kBatch = 8;
+constexpr int kBatch = 14;
 
 // norm of one row, ATen order with 4-element vectors (lane l owns the 8-byte vectors l, l+32, ...)
 __device__ __forceinline__ float warp_row_norm(const __nv_bfloat16* row, int C, int lane) {
@@ -163,40 +163,30 @@ __device__ __forceinline__ int block_argmax(const float* v, long long stride, in
 }
 
 // ------------------------------------------------------------------------------------------------ init
-// one CTA per patch: norms, sizes, links, all adjacent similarities
+// links, sizes, flags, dirty lists (norms and similarities come from the streaming cosine kernel of dpselect.cu,
+// which reads the bank once at HBM speed)
 __global__ void __launch_bounds__(kMlThreads) mallm_init_kernel(MallmParams P) {
     pdl_enter();
     __shared__ int s_cnt;
-    const int p = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.x;
     if (threadIdx.x == 0) s_cnt = 0;
     __syncthreads();
-    for (int i = warp; i < P.T; i += kMlWarps) {
-        const float n = warp_row_norm(P.x + ((size_t)i * P.N + p) * (size_t)P.C, P.C, lane);
-        if (lane == 0) {
-            const size_t a = at(P, i, p);
-            P.nrm[a] = n;
-            P.next[a] = i + 1;
-            P.prev[a] = i - 1;
-            P.alive[a] = 1;
-            if (!P.hard) {
-                const float s = P.sizes_in ? __bfloat162float(P.sizes_in[(size_t)i * P.N + p]) : 1.0f;
-                P.size[a] = s;
-                P.in_work[a] = 0;
-                if (s != 1.0f) P.dirty[(size_t)p * P.T + atomicAdd(&s_cnt, 1)] = i;   // not known to be a fixed point
-            }
-            if (P.sync && p == 0) P.touched[i] = 0;
+    for (int i = threadIdx.x; i < P.T; i += blockDim.x) {
+        const size_t a = at(P, i, p);
+        P.next[a] = i + 1;
+        P.prev[a] = i - 1;
+        P.alive[a] = 1;
+        if (i == P.T - 1) P.sim[a] = -INFINITY;
+        if (!P.hard) {
+            const float s = P.sizes_in ? __bfloat162float(P.sizes_in[(size_t)i * P.N + p]) : 1.0f;
+            P.size[a] = s;
+            P.in_work[a] = 0;
+            if (s != 1.0f) P.dirty[(size_t)p * P.T + atomicAdd(&s_cnt, 1)] = i;       // not known to be a fixed point
         }
+        if (P.sync && p == 0) P.touched[i] = 0;
     }
     __syncthreads();
     if (threadIdx.x == 0 && !P.hard) P.n_dirty[p] = s_cnt;
-    for (int i = warp; i < P.T; i += kMlWarps) {
-        float s = -INFINITY;
-        if (i + 1 < P.T) {
-            const __nv_bfloat16* ra = P.x + ((size_t)i * P.N + p) * (size_t)P.C;
-            s = warp_pair_sim(ra, P.nrm[at(P, i, p)], ra + (size_t)P.N * P.C, P.nrm[at(P, i + 1, p)], P.C, lane);
-        }
-        if (lane == 0) P.sim[at(P, i, p)] = s;
-    }
 }
 
 // ----------------------------------------------------------------------------------------------- round
@@ -364,6 +354,196 @@ __global__ void __launch_bounds__(kMlThreads) mallm_rounds_kernel(MallmParams P,
         const int m = block_argmax(sim_s, 1, P.T, s_best);
         if (P.hard) mallm_hard_round(P, p, r, m, sim_s, 1);
         else mallm_soft_round(P, p, r, m, sim_s, 1);
+        __syncthreads();
+    }
+}
+
+
+// Patch-local mode, fast variant: the whole per-patch state (similarities, norms, sizes, links, flags, dirty lists)
+// lives in shared memory for all rounds, and the row work of a round is done by the whole CTA: the merge (and the
+// replay on dirty rows) is element-wise over 256 threads with every load of the round in flight at once, the result
+// goes to the workspace row AND to a shared-memory row buffer from which ONE warp then takes the norm in ATen's order.
+// Only `alive`, `in_work`, `size` (read by the emit kernel) and the rewritten rows go back to global memory.
+constexpr int kRowBufs = 2;      // row tasks handled per batch (merge + one dirty row is the common case)
+
+struct RoundsSmem {
+    float *sim, *nrm, *size;
+    int *next, *prev;
+    short* dirty;                // [2][T]
+    uint8_t* in_work;
+    __nv_bfloat16* rowbuf;       // [kRowBufs][C]
+};
+__host__ __device__ inline size_t rounds_smem_bytes(int T, int C) {
+    return (size_t)T * (5 * 4 + 2 * 2 + 1) + 16 + (size_t)kRowBufs * C * 2 + 16;
+}
+
+__global__ void __launch_bounds__(kMlThreads) mallm_rounds_smem_kernel(MallmParams P, int rounds) {
+    pdl_enter();
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    __shared__ Best s_best[kMlWarps];
+    __shared__ int s_cnt, s_changed[kRowBufs];
+    const int p = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int T = P.T, C = P.C, nv = C >> 2;
+    RoundsSmem S;
+    {
+        uint8_t* q = smem_raw;
+        S.sim = reinterpret_cast<float*>(q);   q += (size_t)T * 4;
+        S.nrm = reinterpret_cast<float*>(q);   q += (size_t)T * 4;
+        S.size = reinterpret_cast<float*>(q);  q += (size_t)T * 4;
+        S.next = reinterpret_cast<int*>(q);    q += (size_t)T * 4;
+        S.prev = reinterpret_cast<int*>(q);    q += (size_t)T * 4;
+        S.dirty = reinterpret_cast<short*>(q); q += (size_t)T * 4;
+        S.in_work = q;                         q += ((size_t)T + 15) & ~(size_t)15;
+        S.rowbuf = reinterpret_cast<__nv_bfloat16*>(q);
+    }
+    for (int i = tid; i < T; i += blockDim.x) {
+        const size_t a = at(P, i, p);
+        S.sim[i] = P.sim[a];
+        S.nrm[i] = P.nrm[a];
+        S.next[i] = P.next[a];
+        S.prev[i] = P.prev[a];
+        if (!P.hard) {
+            S.size[i] = P.size[a];
+            S.in_work[i] = P.in_work[a];
+        }
+    }
+    int nd = 0;
+    if (!P.hard) {
+        nd = P.n_dirty[p];
+        for (int i = tid; i < nd; i += blockDim.x) S.dirty[i] = (short)P.dirty[(size_t)p * T + i];
+    }
+    __syncthreads();
+    auto row = [&](int i) -> const __nv_bfloat16* {
+        const size_t off = ((size_t)i * P.N + p) * (size_t)C;
+        return (!P.hard && S.in_work[i]) ? P.work + off : P.x + off;
+    };
+    for (int r = 0; r < rounds; ++r) {
+        const int m = block_argmax(S.sim, 1, T, s_best);
+        if (P.hard) {
+            if (warp == 0) {
+                const int pm = S.prev[m], n = S.next[m];
+                float sv = 0.f;
+                if (pm >= 0) sv = warp_pair_sim(row(pm), S.nrm[pm], row(n), S.nrm[n], C, lane);
+                if (lane == 0) {
+                    P.alive[at(P, m, p)] = 0;
+                    S.sim[m] = -INFINITY;
+                    S.prev[n] = pm;
+                    if (pm >= 0) {
+                        S.next[pm] = n;
+                        S.sim[pm] = sv;
+                    }
+                }
+            }
+            __syncthreads();
+            continue;
+        }
+        const int n = S.next[m];
+        const short* cur = S.dirty + (size_t)(r & 1) * T;
+        short* nxt = S.dirty + (size_t)((r + 1) & 1) * T;
+        if (tid == 0) s_cnt = 0;
+        // ---- row tasks in batches of kRowBufs: task 0 = merge (m, n) -> m, task k > 0 = replay on dirty row cur[k - 1]
+        for (int t0 = 0; t0 <= nd; t0 += kRowBufs) {
+            if (tid < kRowBufs) s_changed[tid] = 0;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < kRowBufs; ++k) {
+                const int task = t0 + k;
+                if (task > nd) break;
+                const int j = task ? cur[task - 1] : m;
+                if (task && (j == m || j == n)) continue;
+                const uint2* src = reinterpret_cast<const uint2*>(row(j));
+                uint2* dst = reinterpret_cast<uint2*>(P.work + ((size_t)j * P.N + p) * (size_t)C);
+                uint2* buf = reinterpret_cast<uint2*>(S.rowbuf + (size_t)k * C);
+                if (task == 0) {
+                    const uint2* src2 = reinterpret_cast<const uint2*>(row(n));
+                    const float sa = S.size[m], sb = S.size[n];
+                    const float snew = round_bf16(sa + sb);
+                    for (int v0 = tid; v0 < nv; v0 += 4 * kMlThreads) {
+                        uint2 q[4], w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int v = v0 + u * kMlThreads;
+                            if (v < nv) { q[u] = src[v]; w[u] = src2[v]; }
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int v = v0 + u * kMlThreads;
+                            if (v < nv) {
+                                uint2 y;
+                                y.x = merge_pair(q[u].x, w[u].x, sa, sb, snew);
+                                y.y = merge_pair(q[u].y, w[u].y, sa, sb, snew);
+                                dst[v] = y;
+                                buf[v] = y;
+                            }
+                        }
+                    }
+                    if (tid == 0) s_changed[k] = 1;
+                } else {
+                    const float sz = S.size[j];
+                    bool diff = false;
+                    for (int v0 = tid; v0 < nv; v0 += 4 * kMlThreads) {
+                        uint2 q[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int v = v0 + u * kMlThreads;
+                            if (v < nv) q[u] = src[v];
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const int v = v0 + u * kMlThreads;
+                            if (v < nv) {
+                                uint2 y;
+                                y.x = rescale_pair(q[u].x, sz);
+                                y.y = rescale_pair(q[u].y, sz);
+                                diff |= (y.x != q[u].x) || (y.y != q[u].y);
+                                dst[v] = y;
+                                buf[v] = y;
+                            }
+                        }
+                    }
+                    if (diff) s_changed[k] = 1;
+                }
+            }
+            __syncthreads();
+            if (warp < kRowBufs && t0 + warp <= nd) {
+                const int task = t0 + warp;
+                const int j = task ? cur[task - 1] : m;
+                if (!(task && (j == m || j == n))) {
+                    const float nr = warp_row_norm(S.rowbuf + (size_t)warp * C, C, lane);
+                    if (lane == 0) {
+                        S.nrm[j] = nr;
+                        S.in_work[j] = 1;
+                        P.in_work[at(P, j, p)] = 1;
+                        if (s_changed[warp]) nxt[atomicAdd(&s_cnt, 1)] = (short)j;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        if (tid == 0) {                                          // sizes and links
+            const float snew = round_bf16(S.size[m] + S.size[n]);
+            S.size[m] = snew;
+            P.size[at(P, m, p)] = snew;
+            const int nx = S.next[n];
+            S.next[m] = nx;
+            if (nx < T) S.prev[nx] = m;
+            P.alive[at(P, n, p)] = 0;
+            S.sim[n] = -INFINITY;
+        }
+        __syncthreads();
+        // ---- similarities on both sides of every changed row
+        const int nch = s_cnt;
+        for (int task = warp; task < 2 * nch; task += kMlWarps) {
+            const int j = nxt[task >> 1];
+            int a, b;
+            if (task & 1) { a = j; b = S.next[j]; }
+            else { a = S.prev[j]; b = j; }
+            if (a < 0) continue;
+            float sv = -INFINITY;
+            if (b < T) sv = warp_pair_sim(row(a), S.nrm[a], row(b), S.nrm[b], C, lane);
+            if (lane == 0) S.sim[a] = sv;
+        }
+        nd = nch;
         __syncthreads();
     }
 }
@@ -582,6 +762,10 @@ extern "C" int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T
         cudaError_t e = cudaFuncSetAttribute(mallm_sync_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
         if (e != cudaSuccess) return (int)e;
     }
+    if (T >= 2) {
+        const int rc = dpselect_sim_nrm(x, T, N, C, DisAux{P.sim, P.nrm, P.si, P.sp}, stream);
+        if (rc) return rc;
+    }
     RTK_LAUNCH_PDL(mallm_init_kernel, (unsigned)N, kMlThreads, 0, stream, P);
     if (sync && t < T) {
         RTK_LAUNCH_PDL(mallm_sync_argmax_kernel, 1, 1024, scan_smem, stream, P, 0);
@@ -589,7 +773,17 @@ extern "C" int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T
     const int rounds = (int)(T - t);
     if (!sync) {
         if (rounds > 0) {
-            RTK_LAUNCH_PDL(mallm_rounds_kernel, (unsigned)N, kMlThreads, scan_smem, stream, P, rounds);
+            int dev = 0, smem_max = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+            const size_t need = rounds_smem_bytes((int)T, (int)C);
+            if (need + 1024 <= (size_t)smem_max) {                 // whole per-patch state in shared memory
+                cudaError_t e2 = cudaFuncSetAttribute(mallm_rounds_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need);
+                if (e2 != cudaSuccess) return (int)e2;
+                RTK_LAUNCH_PDL(mallm_rounds_smem_kernel, (unsigned)N, kMlThreads, need, stream, P, rounds);
+            } else {                                              // very long videos: state stays in global memory
+                RTK_LAUNCH_PDL(mallm_rounds_kernel, (unsigned)N, kMlThreads, scan_smem, stream, P, rounds);
+            }
         }
     } else {
         for (int r = 0; r < rounds; ++r) {

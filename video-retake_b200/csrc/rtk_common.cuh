@@ -21,6 +21,15 @@ extern long long g_launches;  // host-side launch counter (rtk_launch_count)
 
 constexpr int kWarp = 32;
 
+// optional outputs of the streaming cosine kernel (dpselect.cu) used by the MA-LLM compressors (mallm.cu):
+// sim[i * si + p * sp] = bf16 cosine(frame i, frame i + 1), nrm[i * si + p * sp] = clamped bf16 norm of frame i
+struct DisAux {
+    float* sim;
+    float* nrm;
+    long long si, sp;
+};
+int dpselect_sim_nrm(const void* x, int64_t T, int64_t N, int64_t C, DisAux aux, cudaStream_t st);
+
 // ------------------------------------------------------------------------ programmatic dependent launch (PDL)
 // The operators are chains of small dependent kernels on one stream.  Launched with the programmatic-stream-
 // serialization attribute a kernel may become resident while its predecessor is still running; every kernel
