@@ -48,7 +48,7 @@ struct RowCursor {
 };
 
 // short rows (K4 <= 16, <= 120 registers) run two CTAs per SM so that 16 warps hide the per-row reduction latency
-template <int K4>
+template <int K4, bool AUX>
 __global__ void __launch_bounds__(kDisThreads, (K4 <= 16) ? 2 : 1)
 dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis, int T, int N, int C, int R,
                     int n_items, int stages, int halo, DisAux aux) {
@@ -112,7 +112,9 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
 
         float nrm = round_bf16(__fsqrt_rn(ss));
         nrm = fmaxf(nrm, eps);
-        if (aux.nrm && lane == 0) aux.nrm[(size_t)cons.f * aux.si + (size_t)cons.p * aux.sp] = nrm;
+        if (AUX) {
+            if (lane == 0) aux.nrm[(size_t)cons.f * aux.si + (size_t)cons.p * aux.sp] = nrm;
+        }
         const float rcp = __frcp_rn(nrm);
 #pragma unroll
         for (int k = 0; k < K4; ++k) {
@@ -148,10 +150,10 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
             v += __shfl_down_sync(0xffffffffu, v, 4);        // offset 2
             v += __shfl_down_sync(0xffffffffu, v, 2);        // offset 1  -> 8-lane 0 == physical lane 1
             if (lane == 1) {
-                if (aux.sim) aux.sim[(size_t)(cons.f - 1) * aux.si + (size_t)cons.p * aux.sp] = round_bf16(v);   // MA-LLM state
+                if (AUX) aux.sim[(size_t)(cons.f - 1) * aux.si + (size_t)cons.p * aux.sp] = round_bf16(v);   // MA-LLM state
                 else dis[(size_t)(cons.f - halo) * N + cons.p] = 1.0f - round_bf16(v);
             }
-        } else if (cons.f == 0 && !halo && !aux.sim) {
+        } else if (!AUX && cons.f == 0 && !halo) {
             if (lane == 0) dis[cons.p] = 1.0f;
         }
         ++consumed;
@@ -170,7 +172,7 @@ __global__ void fill_f32_kernel(float* p, int n, float v) {
     if (i < n) p[i] = v;
 }
 
-template <int K4>
+template <int K4, bool AUX = false>
 static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, cudaStream_t st, DisAux aux = DisAux{nullptr, nullptr, 0, 0}) {
     int dev = 0, sms = 0, smem_max = 0;
     cudaGetDevice(&dev);
@@ -193,7 +195,7 @@ static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, 
     const long long n_items = runs * N;
     long long grid = (n_items + kDisWarps - 1) / kDisWarps;
     if (grid > (long long)sms * ctas_per_sm) grid = (long long)sms * ctas_per_sm;
-    auto kern = dpselect_dis_kernel<K4>;
+    auto kern = dpselect_dis_kernel<K4, AUX>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kDisThreads, smem, st>>>((const __nv_bfloat16*)x, dis, T, N, C, (int)R, (int)n_items,
@@ -424,14 +426,14 @@ gather_rows_kernel(const uint4* __restrict__ x, const long long* __restrict__ sr
 int dpselect_sim_nrm(const void* x, int64_t T, int64_t N, int64_t C, DisAux aux, cudaStream_t st) {
     if (T < 2) return RTK_E_BADARG;
     const int k4 = (int)((C / 4 + 31) / 32);
-    if (k4 <= 2) return launch_dis<2>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
-    if (k4 <= 4) return launch_dis<4>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
-    if (k4 <= 9) return launch_dis<9>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
-    if (k4 <= 16) return launch_dis<16>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
-    if (k4 <= 28) return launch_dis<28>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
-    if (k4 <= 32) return launch_dis<32>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
-    if (k4 <= 48) return launch_dis<48>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
-    return launch_dis<64>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 2) return launch_dis<2, true>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 4) return launch_dis<4, true>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 9) return launch_dis<9, true>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 16) return launch_dis<16, true>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 28) return launch_dis<28, true>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 32) return launch_dis<32, true>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    if (k4 <= 48) return launch_dis<48, true>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
+    return launch_dis<64, true>(x, (int)T, (int)N, (int)C, 0, nullptr, st, aux);
 }
 
 }  // namespace rtk
