@@ -48,7 +48,7 @@ struct RowCursor {
 };
 
 // short rows (K4 <= 16, <= 120 registers) run two CTAs per SM so that 16 warps hide the per-row reduction latency
-template <int K4, bool AUX>
+template <int K4, bool AUX, bool EXACT>   // EXACT: C == K4 * 128, every lane owns K4 full vectors (no bounds checks)
 __global__ void __launch_bounds__(kDisThreads, (K4 <= 16) ? 2 : 1)
 dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis, int T, int N, int C, int R,
                     int n_items, int stages, int halo, DisAux aux) {
@@ -93,7 +93,7 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
 #pragma unroll
         for (int k = 0; k < K4; ++k) {
             const int v = lane + 32 * k;
-            cur[k] = (v < nv4) ? *reinterpret_cast<const uint2*>(row + 8 * v) : make_uint2(0u, 0u);
+            cur[k] = (EXACT || v < nv4) ? *reinterpret_cast<const uint2*>(row + 8 * v) : make_uint2(0u, 0u);
         }
         // ---- norm: 4 accumulators per lane, sequential over k (ATen Reduce.cuh, input_vec_size 4)
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -195,7 +195,7 @@ static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, 
     const long long n_items = runs * N;
     long long grid = (n_items + kDisWarps - 1) / kDisWarps;
     if (grid > (long long)sms * ctas_per_sm) grid = (long long)sms * ctas_per_sm;
-    auto kern = dpselect_dis_kernel<K4, AUX>;
+    auto kern = (!AUX && C == K4 * 128) ? dpselect_dis_kernel<K4, AUX, !AUX> : dpselect_dis_kernel<K4, AUX, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kDisThreads, smem, st>>>((const __nv_bfloat16*)x, dis, T, N, C, (int)R, (int)n_items,
