@@ -28,8 +28,27 @@ for p in (ROOT, os.path.join(ROOT, "video-retake_b200"), os.path.join(ROOT, "tes
     if p not in sys.path:
         sys.path.insert(0, p)
 
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"                   # keep stdout to the one JSON line
+# stdout carries exactly ONE JSON line: whatever libraries print while the run is in progress (NCCL's version banner,
+# transformers' notices ...) is sent to stderr by pointing fd 1 at fd 2 until the line is ready (emit()).
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(obj), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
+
 
 import torch  # noqa: E402
 
@@ -254,6 +273,7 @@ def cpu_reference_step(s, sample_T, host, it):
 
 def main():
     a = parse()
+    quiet_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -282,7 +302,7 @@ def main():
         val = s.frames / sec
         sample = (f"per step: DPSelect on {sample_T} of {s.T} temporal grids + 1 of {s.chunks * s.layers} compressing updates "
                   f"at L={s.L}, scaled linearly to the whole video (extrapolated)")
-        print(json.dumps({"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        emit(({"metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
                           "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "bf16", "data": "synthetic", "impl": "reference", "config": config,
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
@@ -433,7 +453,7 @@ def main():
         line["cpu_baseline"] = {"value": s.frames / sec, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": (f"DPSelect on 64 of {s.T} grids ({td:.2f} s) + 1 of {s.chunks * s.layers} compressing "
                                            f"updates at L={s.L} ({tu:.2f} s), scaled linearly (extrapolated)")}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
