@@ -197,6 +197,17 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
 // bf16x2 -> (lo, hi) widened to fp32, packed for the x2 pipes
 __device__ __forceinline__ uint64_t widen2(uint32_t p) { return pk2(bf16lo_to_f32(p), bf16hi_to_f32(p)); }
 
+#ifndef RTK_SCORE_FEEDER_SLEEP
+#define RTK_SCORE_FEEDER_SLEEP 0     // ns the TMA / MMA warps sleep between mbarrier polls (0: spin)
+#endif
+// wait used by the producer and MMA-issuer warps: they share their scheduler with four softmax warps, and a tight poll
+// loop takes issue slots away from them
+__device__ __forceinline__ void mbar_wait_feeder(uint32_t bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+        if (RTK_SCORE_FEEDER_SLEEP > 0) __nanosleep(RTK_SCORE_FEEDER_SLEEP);
+    }
+}
+
 #ifndef RTK_SCORE_RZPACK
 #define RTK_SCORE_RZPACK 1     // round to bf16 in place (F2FP with a zero low half: the result IS the fp32 value; default, -5 %) vs pack + widen (0)
 #endif
@@ -432,7 +443,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 const int h = u / nt, ta = u - h * nt;
                 const int a_head = (PASS == 1) ? h : h / prm.G;
                 const int b_head = (PASS == 1) ? h / prm.G : h;
-                mbar_wait(a_empty, (ucnt & 1u) ^ 1u);
+                mbar_wait_feeder(a_empty, (ucnt & 1u) ^ 1u);
                 mbar_arrive_expect_tx(a_full, prm.n_atoms * kHalfBytes);
                 for (int kk = 0; kk < prm.n_atoms; ++kk) {
                     const int row = ta * kTile;
@@ -442,7 +453,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 ++ucnt;
                 for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                     const int s = cnt % kStages;
-                    mbar_wait(b_empty(s), ((cnt / kStages) & 1u) ^ 1u);
+                    mbar_wait_feeder(b_empty(s), ((cnt / kStages) & 1u) ^ 1u);
                     mbar_arrive_expect_tx(b_full(s), prm.n_atoms * kHalfBytes);
                     const uint32_t dst = base + ScoreSmem::b_ring + s * kTileBytes;
                     for (int kk = 0; kk < prm.n_atoms; ++kk) {
@@ -465,12 +476,12 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
         // ======================================================================= MMA issuer
         uint32_t cnt = 0, ucnt = 0;
         while (range.next(u, tb0, tb1)) {
-            mbar_wait(a_full, ucnt & 1u);
+            mbar_wait_feeder(a_full, ucnt & 1u);
             ++ucnt;
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 const int s = cnt % kStages, b = cnt % kAccBufs;
-                mbar_wait(b_full(s), (cnt / kStages) & 1u);
-                mbar_wait(t_empty(b), ((cnt / kAccBufs) & 1u) ^ 1u);
+                mbar_wait_feeder(b_full(s), (cnt / kStages) & 1u);
+                mbar_wait_feeder(t_empty(b), ((cnt / kAccBufs) & 1u) ^ 1u);
                 tc_fence_after();
                 if (elect_one()) {
                     const uint32_t a0 = base + ScoreSmem::a_tile, b0 = base + ScoreSmem::b_ring + s * kTileBytes;
