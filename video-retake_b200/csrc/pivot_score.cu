@@ -11,8 +11,12 @@
 // Because the softmax side owns whole TMEM lanes, pass 1 reduces along columns inside a thread (no shuffles)
 // and pass 2 accumulates the column sums inside a thread as well - hence the transposed second pass.
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane),
-// warps 2-5 and 6-9 two softmax groups that take alternate accumulator tiles.
+// Warp roles (576 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane), warps 2-17
+// four softmax groups of four warps (one warp per TMEM lane quarter): accumulator tile n goes to groups 2(n&1) and
+// 2(n&1)+1, each taking 64 of its 128 columns with one tcgen05.ld.32x32b.x64.  Per logit the softmax side issues two
+// in-place fp32->bf16 roundings (F2FP with a zero low half), packed f32x2 scale / FMA / add, one MUFU.EX2 and (pass 1)
+// half an FMNMX3; what bounds it is the MUFU pipe and the softmax warps' issue slots (profiles/r1_score_ab_experiments.md).
+// Every -DRTK_SCORE_* flag below is an A/B switch documented there; the defaults are the shipped configuration.
 #include <cuda.h>
 
 #include "rtk_common.cuh"
