@@ -341,7 +341,8 @@ __device__ __forceinline__ float aten_row_sum_f32(const float* __restrict__ row,
 
 // sync == 1: per-frame mean over patches (ATen mean: fp32 sum in Reduce.cuh order with 4-element vectors,
 // times fp32(1/N)), then one warp selects frames; the mask row of each kept frame is replicated N times.
-__global__ void __launch_bounds__(kSelWarps * kWarp)
+constexpr int kSyncWarps = 32;    // one CTA; 32 row means in flight instead of 8 (the means are a chain of DRAM round trips)
+__global__ void __launch_bounds__(kSyncWarps * kWarp)
 dpselect_select_sync_kernel(const float* __restrict__ dis, int T, int N, int t, int32_t* __restrict__ idx,
                             uint8_t* __restrict__ mask) {
     extern __shared__ __align__(128) uint8_t smem[];
@@ -350,7 +351,7 @@ dpselect_select_sync_kernel(const float* __restrict__ dis, int T, int N, int t, 
     int32_t* sel = reinterpret_cast<int32_t*>(smem + (size_t)T * 4 + (((size_t)T + 15) & ~(size_t)15));  // [t]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float rcpN = 1.0f / (float)N;
-    for (int tt = warp; tt < T; tt += kSelWarps) {
+    for (int tt = warp; tt < T; tt += kSyncWarps) {
         const float s = aten_row_sum_f32(dis + (size_t)tt * N, N, lane);
         if (lane == 0) d[tt] = s * rcpN;
     }
@@ -370,7 +371,17 @@ dpselect_select_sync_kernel(const float* __restrict__ dis, int T, int N, int t, 
         });
     }
     __syncthreads();
-    for (size_t i = threadIdx.x; i < (size_t)t * N; i += blockDim.x) mask[i] = pk[sel[i / N]];
+    // mask row of kept frame j = its peak flag, N times: 16-byte stores where the row allows it
+    for (int j = warp; j < t; j += kSyncWarps) {
+        const uint8_t f = pk[sel[j]];
+        uint8_t* row = mask + (size_t)j * N;
+        const int head = min(N, (int)((16 - ((uintptr_t)row & 15)) & 15));
+        const int body = (N - head) >> 4;
+        const uint4 w = make_uint4(f * 0x01010101u, f * 0x01010101u, f * 0x01010101u, f * 0x01010101u);
+        for (int i = lane; i < head; i += 32) row[i] = f;
+        for (int i = lane; i < body; i += 32) reinterpret_cast<uint4*>(row + head)[i] = w;
+        for (int i = head + body * 16 + lane; i < N; i += 32) row[i] = f;
+    }
 }
 
 // ============================================================================================== A3: gather
@@ -475,7 +486,7 @@ extern "C" int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64
         cudaError_t e = cudaFuncSetAttribute(dpselect_select_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)smem);
         if (e != cudaSuccess) return (int)e;
-        dpselect_select_sync_kernel<<<1, kSelWarps * kWarp, smem, st>>>(dis, (int)T, (int)N, (int)t, idx, mask);
+        dpselect_select_sync_kernel<<<1, kSyncWarps * kWarp, smem, st>>>(dis, (int)T, (int)N, (int)t, idx, mask);
     } else {
         const size_t smem = (size_t)kSelWarps * T * 5;
         cudaError_t e = cudaFuncSetAttribute(dpselect_select_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
