@@ -36,6 +36,10 @@ namespace rtk {
 constexpr int kTile = 128;            // rows of both operand tiles, = UMMA M = UMMA N
 constexpr int kHeadDim = 128;         // largest D: two 64-element swizzle atoms (D = 64 uses one)
 constexpr int kStages = 4;            // streamed-operand ring
+#ifndef RTK_SCORE_ASLOTS
+#define RTK_SCORE_ASLOTS 2            // stationary-tile slots: 2 = the next unit's tile is fetched while this unit still computes
+#endif
+constexpr int kASlots = RTK_SCORE_ASLOTS;
 constexpr int kAccBufs = 4;           // 128-column TMEM buffers
 constexpr int kStatSlots = 8;         // pass 2: per-tile c_q rows (see ring-distance argument in DESIGN.md)
 constexpr uint32_t kTileBytes = kTile * kHeadDim * 2;        // 32 KiB
@@ -43,13 +47,13 @@ constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] sw
 
 struct ScoreSmem {
     // offsets inside dynamic shared memory (1024-byte aligned base)
-    static constexpr uint32_t a_tile = 0;
-    static constexpr uint32_t b_ring = kTileBytes;
+    static constexpr uint32_t a_tile = 0;                                             // [kASlots] stationary tiles
+    static constexpr uint32_t b_ring = kASlots * kTileBytes;
     static constexpr uint32_t stats = b_ring + kStages * kTileBytes;                 // [kStatSlots][128] f32
     static constexpr uint32_t merge = stats + kStatSlots * kTile * 4;                // [4][128][2] f32
     static constexpr uint32_t bars = merge + 8 * kTile * 2 * 4;          // up to 8 groups
-    // barriers: a_full, a_empty, b_full[4], b_empty[4], t_full[4], t_empty[4], st_full[8], port
-    static constexpr uint32_t n_bars = 2 + 2 * kStages + 2 * kAccBufs + kStatSlots + 1;
+    // barriers: a_full[2], a_empty[2], b_full[4], b_empty[4], t_full[4], t_empty[4], st_full[8], port
+    static constexpr uint32_t n_bars = 4 + 2 * kStages + 2 * kAccBufs + kStatSlots + 1;
     static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
     static constexpr uint32_t total = tmem_ptr + 16;
 };
@@ -405,17 +409,17 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     const uint32_t bar0 = base + ScoreSmem::bars;
-    const uint32_t a_full = bar0, a_empty = bar0 + 8;
-    auto b_full = [&](int s) { return bar0 + 16 + 8 * s; };
-    auto b_empty = [&](int s) { return bar0 + 16 + 8 * (kStages + s); };
-    auto t_full = [&](int b) { return bar0 + 16 + 8 * (2 * kStages + b); };
-    auto t_empty = [&](int b) { return bar0 + 16 + 8 * (2 * kStages + kAccBufs + b); };
-    auto st_full = [&](int i) { return bar0 + 16 + 8 * (2 * kStages + 2 * kAccBufs + i); };
-    const uint32_t port = bar0 + 16 + 8 * (2 * kStages + 2 * kAccBufs + kStatSlots);
+    auto a_full = [&](int i) { return bar0 + 8 * i; };
+    auto a_empty = [&](int i) { return bar0 + 16 + 8 * i; };
+    auto b_full = [&](int s) { return bar0 + 32 + 8 * s; };
+    auto b_empty = [&](int s) { return bar0 + 32 + 8 * (kStages + s); };
+    auto t_full = [&](int b) { return bar0 + 32 + 8 * (2 * kStages + b); };
+    auto t_empty = [&](int b) { return bar0 + 32 + 8 * (2 * kStages + kAccBufs + b); };
+    auto st_full = [&](int i) { return bar0 + 32 + 8 * (2 * kStages + 2 * kAccBufs + i); };
+    const uint32_t port = bar0 + 32 + 8 * (2 * kStages + 2 * kAccBufs + kStatSlots);
 
     if (threadIdx.x == 0) {
-        mbar_init(a_full, 1);
-        mbar_init(a_empty, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
         for (int s = 0; s < kStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int b = 0; b < kAccBufs; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), kTileArrivals); }
         for (int i = 0; i < kStatSlots; ++i) mbar_init(st_full(i), 1);
@@ -447,12 +451,15 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 const int h = u / nt, ta = u - h * nt;
                 const int a_head = (PASS == 1) ? h : h / prm.G;
                 const int b_head = (PASS == 1) ? h / prm.G : h;
-                mbar_wait_feeder(a_empty, (ucnt & 1u) ^ 1u);
-                mbar_arrive_expect_tx(a_full, prm.n_atoms * kHalfBytes);
+                // stationary tile of this unit into slot ucnt % kASlots: with two slots it is on its way while the
+                // MMAs of the previous unit are still running (no pipeline bubble at unit boundaries)
+                const int as = ucnt % kASlots;
+                mbar_wait_feeder(a_empty(as), ((ucnt / kASlots) & 1u) ^ 1u);
+                mbar_arrive_expect_tx(a_full(as), prm.n_atoms * kHalfBytes);
                 for (int kk = 0; kk < prm.n_atoms; ++kk) {
                     const int row = ta * kTile;
-                    tma_load_3d(base + ScoreSmem::a_tile + kk * kHalfBytes, a_map, kk * 64, a_l1 ? row : a_head,
-                                a_l1 ? a_head : row, a_full);
+                    tma_load_3d(base + ScoreSmem::a_tile + as * kTileBytes + kk * kHalfBytes, a_map, kk * 64, a_l1 ? row : a_head,
+                                a_l1 ? a_head : row, a_full(as));
                 }
                 ++ucnt;
                 for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
@@ -480,7 +487,8 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
         // ======================================================================= MMA issuer
         uint32_t cnt = 0, ucnt = 0;
         while (range.next(u, tb0, tb1)) {
-            mbar_wait_feeder(a_full, ucnt & 1u);
+            const int as = ucnt % kASlots;
+            mbar_wait_feeder(a_full(as), (ucnt / kASlots) & 1u);
             ++ucnt;
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 const int s = cnt % kStages, b = cnt % kAccBufs;
@@ -488,7 +496,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                 mbar_wait_feeder(t_empty(b), ((cnt / kAccBufs) & 1u) ^ 1u);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint32_t a0 = base + ScoreSmem::a_tile, b0 = base + ScoreSmem::b_ring + s * kTileBytes;
+                    const uint32_t a0 = base + ScoreSmem::a_tile + as * kTileBytes, b0 = base + ScoreSmem::b_ring + s * kTileBytes;
                     const int nks = prm.n_atoms * 4;
 #pragma unroll 8
                     for (int ks = 0; ks < nks; ++ks) {
@@ -498,7 +506,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                     }
                     tc_commit(b_empty(s));
                     tc_commit(t_full(b));
-                    if (tb == tb1 - 1) tc_commit(a_empty);
+                    if (tb == tb1 - 1) tc_commit(a_empty(as));
                 }
                 __syncwarp();
             }
