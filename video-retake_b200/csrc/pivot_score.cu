@@ -35,13 +35,17 @@ namespace rtk {
 
 constexpr int kTile = 128;            // rows of both operand tiles, = UMMA M = UMMA N
 constexpr int kHeadDim = 128;         // largest D: two 64-element swizzle atoms (D = 64 uses one)
-constexpr int kStages = 4;            // streamed-operand ring
+#ifndef RTK_SCORE_STAGES
+#define RTK_SCORE_STAGES 4            // streamed-operand ring depth
+#endif
+constexpr int kStages = RTK_SCORE_STAGES;
 #ifndef RTK_SCORE_ASLOTS
 #define RTK_SCORE_ASLOTS 2            // stationary-tile slots: 2 = the next unit's tile is fetched while this unit still computes
 #endif
 constexpr int kASlots = RTK_SCORE_ASLOTS;
 constexpr int kAccBufs = 4;           // 128-column TMEM buffers
-constexpr int kStatSlots = 8;         // pass 2: per-tile c_q rows (see ring-distance argument in DESIGN.md)
+constexpr int kStatSlots = kStages + kAccBufs;   // pass 2: per-tile c_q rows; a slot is rewritten for tile c after MMA(c - kStages)
+                                                 // was issued, i.e. after tile c - kStages - kAccBufs left the softmax side
 constexpr uint32_t kTileBytes = kTile * kHeadDim * 2;        // 32 KiB
 constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] swizzle-128B box
 
