@@ -44,8 +44,14 @@ constexpr int kStages = RTK_SCORE_STAGES;
 #endif
 constexpr int kASlots = RTK_SCORE_ASLOTS;
 constexpr int kAccBufs = 4;           // 128-column TMEM buffers
-constexpr int kStatSlots = kStages + kAccBufs;   // pass 2: per-tile c_q rows; a slot is rewritten for tile c after MMA(c - kStages)
-                                                 // was issued, i.e. after tile c - kStages - kAccBufs left the softmax side
+#ifndef RTK_SCORE_EARLY_RELEASE
+#define RTK_SCORE_EARLY_RELEASE 0     // 1: hand the accumulator buffer back as soon as it sits in registers (A/B: no gain)
+#endif
+// pass 2: per-tile c_q rows.  A slot is rewritten for tile c after MMA(c - kStages) was issued, i.e. after tile
+// c - kStages - kAccBufs was released by the softmax side.  Released = processed without early release; with it a warp
+// has only finished the tile BEFORE the one it released (c - kStages - kAccBufs - 2 of the same group pair, one more
+// for the other pair), hence four more slots.
+constexpr int kStatSlots = kStages + kAccBufs + (RTK_SCORE_EARLY_RELEASE ? 4 : 0);
 constexpr uint32_t kTileBytes = kTile * kHeadDim * 2;        // 32 KiB
 constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] swizzle-128B box
 
@@ -599,6 +605,11 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
 #if RTK_SCORE_PORT
                     if (lane == 0) mbar_arrive(port);
 #endif
+#if RTK_SCORE_EARLY_RELEASE
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty(b));    // the MMA of tile cnt + 4 may overwrite the buffer now
+#endif
                     softmax_cols<PASS, 64>(r, 0, valid, st, cq, inv, inv2, l2e2);
                 }
 #elif RTK_SCORE_X32DB
@@ -619,9 +630,11 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                     softmax_cols<PASS, 32>(r, c * 32, valid, st, cq, inv, inv2, l2e2);
                 }
 #endif
+#if !(RTK_SCORE_EARLY_RELEASE && RTK_SCORE_X64 && !RTK_SCORE_X16)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty(b));
+#endif
             }
 #endif
             const float m = st.m;
