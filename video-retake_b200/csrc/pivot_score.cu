@@ -377,6 +377,9 @@ __device__ __forceinline__ void softmax_cols(uint32_t (&r)[NC], int col0, int va
 
 // One CTA's share of the flattened (unit, streamed tile) space: a contiguous range, so every SM gets the same
 // number of tile-steps (+-1) and a unit is shared by at most two CTAs (range length >= nt).
+#ifndef RTK_SCORE_EVEN_RANGES
+#define RTK_SCORE_EVEN_RANGES 0     // 1: even-aligned tile ranges (A/B: no gain)
+#endif
 struct TileRange {
     long long g, g1;
     int nt;
@@ -384,6 +387,14 @@ struct TileRange {
         const long long G = (long long)H * nt_ * nt_;
         g = G * blockIdx.x / gridDim.x;
         g1 = G * (blockIdx.x + 1) / gridDim.x;
+#if RTK_SCORE_EVEN_RANGES
+        // consecutive tiles alternate between the two softmax group pairs: with an even number of tiles per unit every
+        // (partial) unit of an even-aligned range gives both pairs the same amount of work before they meet at the merge
+        if ((nt_ & 1) == 0) {
+            g = 2 * ((G / 2) * blockIdx.x / gridDim.x);
+            g1 = 2 * ((G / 2) * (blockIdx.x + 1) / gridDim.x);
+        }
+#endif
     }
     __device__ __forceinline__ bool next(int& u, int& tb0, int& tb1) {
         if (g >= g1) return false;
