@@ -6,6 +6,7 @@
  * ctypes binding in the reference's own modules would call (INTEGRATION.md shows that binding):
  *
  *   retake/visual_compression.py:86-177   memory_bank_compress_keyframe   -> rtk_dpselect_*
+ *   retake/visual_compression.py:5-83     memory_bank_compress_MALLM[_hard] (+ the callers' loops) -> rtk_mallm_*
  *   retake/longvideo_cache.py:217-323     PivotKVCache.update             -> rtk_pivot_*
  *
  * Conventions
@@ -14,7 +15,10 @@
  *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it: no allocation, no
  *     host synchronisation, no global state; the caller owns every buffer including `workspace`;
  *   - return value: 0 = ok; >0 = cudaError_t from a launch; <0 = RTK_E_* argument error
- *     (rtk_error_string() turns either into text).
+ *     (rtk_error_string() turns either into text);
+ *   - the PivotKV and MA-LLM kernels are launched with programmatic dependent launch (each kernel waits for its
+ *     predecessor on the stream with griddepcontrol.wait before touching memory); RTK_NO_PDL=1 in the environment
+ *     of the process falls back to plain launches.
  */
 #ifndef RTK_B200_H_
 #define RTK_B200_H_
