@@ -20,7 +20,10 @@
 namespace rtk {
 
 // ============================================================================================ A1: distance
-constexpr int kDisWarps = 8;
+#ifndef RTK_DIS_WARPS
+#define RTK_DIS_WARPS 8
+#endif
+constexpr int kDisWarps = RTK_DIS_WARPS;
 constexpr int kDisThreads = kDisWarps * kWarp;
 
 struct RowCursor {
