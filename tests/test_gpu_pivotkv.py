@@ -383,3 +383,47 @@ def test_update_single_token_tail_chunk(reforge):
     assert cache.last_keep_indices.tolist() == [0] and cache.layers[0].keys.shape[2] == 65
     if reforge:
         assert cache.position_cache[0].shape == (1, 65)
+
+
+@pytest.mark.parametrize("mrope", [[16, 24, 24], None])
+@pytest.mark.parametrize("reverse", [False, True])
+def test_reference_named_rotary_helpers(mrope, reverse):
+    """`apply_multimodal_rotary_pos_emb` / `apply_rotary_pos_emb` keep the reference's signatures (longvideo_cache.py:36-116)
+    and its bf16 expression, bit for bit, in both tensor layouts."""
+    from retake import longvideo_cache as lc
+    g = torch.Generator().manual_seed(17)
+    H, KVH, L, D = 6, 2, 300, 128
+    q = torch.randn(1, H, L, D, generator=g).to(torch.bfloat16).cuda()
+    k = torch.randn(1, KVH, L, D, generator=g).to(torch.bfloat16).cuda()
+    rot = TableRotary(D, mrope=mrope is not None)
+    rot.inv_freq = rot.inv_freq.cuda()
+    ar = torch.arange(L, device="cuda")
+    pos = torch.stack([3 + ar // 64, (ar % 64) // 8, ar % 8])[:, None] if mrope else ar[None]
+    cos, sin = rot(k, pos)
+    scaling = rot.attention_scaling
+
+    def want(x):
+        if mrope:
+            parts_c, parts_s = cos.split(mrope * 2, dim=-1), sin.split(mrope * 2, dim=-1)
+            c = torch.cat([m[i % 3] for i, m in enumerate(parts_c)], dim=-1).unsqueeze(1)
+            s = torch.cat([m[i % 3] for i, m in enumerate(parts_s)], dim=-1).unsqueeze(1)
+        else:
+            c, s = cos.unsqueeze(1), sin.unsqueeze(1)
+        if reverse:
+            return ((x * c) - (lc.rotate_half(x) * s)) / scaling ** 2
+        return (x * c) + (lc.rotate_half(x) * s)
+
+    if mrope:
+        gq, gk = lc.apply_multimodal_rotary_pos_emb(q, k, cos, sin, mrope, reverse=reverse, attention_scaling=scaling)
+        tq, tk = lc.apply_multimodal_rotary_pos_emb(q.transpose(1, 2), k.transpose(1, 2), cos, sin, mrope, unsqueeze_dim=2,
+                                                    reverse=reverse, attention_scaling=scaling)
+    else:
+        gq, gk = lc.apply_rotary_pos_emb(q, k, cos, sin, reverse=reverse, attention_scaling=scaling)
+        tq, tk = lc.apply_rotary_pos_emb(q.transpose(1, 2), k.transpose(1, 2), cos, sin, unsqueeze_dim=2, reverse=reverse,
+                                         attention_scaling=scaling)
+    assert torch.equal(gq, want(q)) and torch.equal(gk, want(k))
+    assert torch.equal(tq.transpose(1, 2), gq) and torch.equal(tk.transpose(1, 2), gk)
+    if not reverse:
+        only_k = (lc.apply_multimodal_rotary_pos_emb(None, k, cos, sin, mrope) if mrope
+                  else lc.apply_rotary_pos_emb(None, k, cos, sin))
+        assert only_k[0] is None and torch.equal(only_k[1], gk)

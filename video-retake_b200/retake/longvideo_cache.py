@@ -35,8 +35,8 @@ from . import _native as N
 
 logger = logging.get_logger(__name__)
 
-__all__ = ["PivotKVCache", "build_kvcache", "repeat_kv", "rotate_half", "pivot_head_scores", "pivot_select",
-           "pivot_compact", "pivot_rope", "pivot_rope_tables"]
+__all__ = ["PivotKVCache", "build_kvcache", "repeat_kv", "rotate_half", "apply_multimodal_rotary_pos_emb",
+           "apply_rotary_pos_emb", "pivot_head_scores", "pivot_select", "pivot_compact", "pivot_rope", "pivot_rope_tables"]
 
 
 # ----------------------------------------------------------------------------------------- thin kernel wrappers
@@ -241,6 +241,33 @@ def repeat_kv(hidden_states: torch.Tensor, n_rep: int) -> torch.Tensor:
 def rotate_half(x: torch.Tensor) -> torch.Tensor:
     h = x.shape[-1] // 2
     return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
+
+
+def _rope_pair(q, k, cos, sin, mrope_section, unsqueeze_dim, reverse, attention_scaling):
+    if unsqueeze_dim not in (1, 2):
+        raise ValueError("unsqueeze_dim must be 1 ([1, heads, L, D]) or 2 ([1, L, heads, D])")
+    if reverse and (q is None or k is None):
+        raise TypeError("reverse rotation needs both q and k (the reference multiplies both unconditionally)")
+
+    def one(x):
+        if x is None:
+            return None
+        view = x if unsqueeze_dim == 1 else x.transpose(1, 2)
+        out = pivot_rope(view, cos, sin, mrope_section, attention_scaling if reverse else 1.0, forward=not reverse)
+        return out if unsqueeze_dim == 1 else out.transpose(1, 2)
+
+    return one(q), one(k)
+
+
+def apply_multimodal_rotary_pos_emb(q, k, cos, sin, mrope_section, unsqueeze_dim=1, reverse=False, attention_scaling=1):
+    """Same signature and bf16 rounding chain as ``longvideo_cache.py:36-83`` (``cos`` / ``sin`` ``[3, 1, L, D]`` from the
+    model's rotary module; ``reverse=True`` un-rotates and divides by ``attention_scaling ** 2``), on ``rtk_pivot_rope``."""
+    return _rope_pair(q, k, cos, sin, list(mrope_section), unsqueeze_dim, reverse, attention_scaling)
+
+
+def apply_rotary_pos_emb(q, k, cos, sin, position_ids=None, unsqueeze_dim=1, reverse=False, attention_scaling=1):
+    """1-D rotary twin of the above (``longvideo_cache.py:86-116``; ``cos`` / ``sin`` ``[1, L, D]``)."""
+    return _rope_pair(q, k, cos, sin, None, unsqueeze_dim, reverse, attention_scaling)
 
 
 class PivotKVLayer(DynamicLayer):
