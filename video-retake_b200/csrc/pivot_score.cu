@@ -51,7 +51,10 @@ constexpr int kAccBufs = 4;           // 128-column TMEM buffers
 // c - kStages - kAccBufs was released by the softmax side.  Released = processed without early release; with it a warp
 // has only finished the tile BEFORE the one it released (c - kStages - kAccBufs - 2 of the same group pair, one more
 // for the other pair), hence four more slots.
-constexpr int kStatSlots = kStages + kAccBufs + (RTK_SCORE_EARLY_RELEASE ? 4 : 0);
+#ifndef RTK_SCORE_PIPE2
+#define RTK_SCORE_PIPE2 0             // pass 2: 32-column TMEM loads software-pipelined across tiles (releases buffers early too)
+#endif
+constexpr int kStatSlots = kStages + kAccBufs + ((RTK_SCORE_EARLY_RELEASE || RTK_SCORE_PIPE2) ? 4 : 0);
 constexpr uint32_t kTileBytes = kTile * kHeadDim * 2;        // 32 KiB
 constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] swizzle-128B box
 
@@ -574,6 +577,65 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                     __syncwarp();
                     if (lane == 0) mbar_arrive(t_empty(b));
                 }
+            }
+#elif RTK_SCORE_PIPE2
+            if (PASS == 2) {
+                // this warp's tiles of the unit: every other one; its 64 columns of a tile arrive as two 32-column loads,
+                // and the load of the NEXT 32 columns (same tile or the pair's next tile) is in flight during the math
+                uint32_t ra[32], rb[32];
+                uint32_t c = cnt + (((cnt & 1u) != (uint32_t)(grp >> 1)) ? 1u : 0u);       // first owned tile counter
+                int tb = tb0 + (int)(c - cnt);
+                auto ready = [&](uint32_t cc) {
+                    mbar_wait(t_full(cc % kAccBufs), (cc / kAccBufs) & 1u);
+                    tc_fence_after();
+                    mbar_wait(st_full(cc % kStatSlots), (cc / kStatSlots) & 1u);
+                };
+                bool have = tb < tb1;
+                if (have) {
+                    ready(c);
+                    tmem_ld32(lane_addr + (c % kAccBufs) * kTile, ra);
+                    tmem_ld_wait();
+                }
+                while (have) {
+                    const int b = c % kAccBufs;
+                    const int valid = prm.L - tb * kTile - half * 64;
+                    const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (c % kStatSlots) * kTile + half * 64;
+                    tmem_ld32(lane_addr + b * kTile + 32, rb);
+                    softmax_cols<PASS, 32>(ra, 0, valid, st, cq, inv, inv2, l2e2);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty(b));            // both halves sit in registers
+                    const bool more = tb + 2 < tb1;
+                    if (more) {
+                        ready(c + 2);
+                        tmem_ld32(lane_addr + ((c + 2) % kAccBufs) * kTile, ra);
+                    }
+                    softmax_cols<PASS, 32>(rb, 32, valid, st, cq, inv, inv2, l2e2);
+                    if (more) tmem_ld_wait();
+                    c += 2;
+                    tb += 2;
+                    have = more;
+                }
+                cnt += (uint32_t)(tb1 - tb0);
+            } else
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                if ((int)(cnt & 1u) != (grp >> 1)) continue;
+                const int b = cnt % kAccBufs;
+                mbar_wait(t_full(b), (cnt / kAccBufs) & 1u);
+                tc_fence_after();
+                const int valid = prm.L - tb * kTile - half * 64;
+                const float* cq = nullptr;
+                const uint32_t taddr = lane_addr + b * kTile;
+                {
+                    uint32_t r[64];
+                    tmem_ld64(taddr, r);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 64>(r, 0, valid, st, cq, inv, inv2, l2e2);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty(b));
             }
 #else
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
