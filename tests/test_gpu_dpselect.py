@@ -176,3 +176,16 @@ def test_full_size_config2_properties():
         else:
             assert torch.equal(out[0], x.gather(0, idx[:, :, None].expand(-1, -1, C)))
         assert int(mask.sum()) <= int(peaks.sum()) * (N if sync else 1)
+
+
+def test_full_size_config4_llava_shape():
+    """BASELINE config 4 shape (SigLIP grid N=729, C=1152), 512 frames: bit-exact against the reference's torch op sequence
+    executed on the same GPU, both modes, incl. the unaligned row means of sync mode (N % 4 != 0)."""
+    from oracle import reference_ops as ro
+    vc = _mods()
+    T, N, C = 512, 729, 1152
+    x = make_video("scene", T, N, C, 31)
+    for t, sync in ((512, False), (256, False), (128, True)):
+        out, mask, idx = vc.memory_bank_compress_keyframe(x[None], t, 3, sync=sync, return_indices=True)
+        want_out, want_mask, want_idx = ro.dpselect(x[None], t, sync)
+        assert torch.equal(idx.long(), want_idx) and torch.equal(mask, want_mask) and torch.equal(out, want_out)
