@@ -427,3 +427,45 @@ def test_reference_named_rotary_helpers(mrope, reverse):
         only_k = (lc.apply_multimodal_rotary_pos_emb(None, k, cos, sin, mrope) if mrope
                   else lc.apply_rotary_pos_emb(None, k, cos, sin))
         assert only_k[0] is None and torch.equal(only_k[1], gk)
+
+
+@pytest.mark.parametrize("reforge", [False, True])
+def test_update_full_size_llava_shape(reforge):
+    """LLaVA-Video shape: L = 6272 tokens per chunk (32 frames x 196), 1-D rotary positions ([1, L], no mrope), then the
+    one-token tail chunk the reference produces when frames % 32 == 0 (llava_onevision.py:157-160)."""
+    lc = _lc()
+    H, KVH, L, D, ratio = 28, 4, 6272, 128, 0.2
+    rot = TableRotary(D, mrope=False)
+    rot.inv_freq = rot.inv_freq.cuda()
+    cache = lc.PivotKVCache(_cfg(H, KVH, D, 1, ratio, reforge))
+    past = 0
+    for Lc, seed in ((L, 300), (1, 301)):
+        keep = max(1, int(ratio * Lc))
+        q, k, v = qkv(H, KVH, Lc, D, 2.0, seed=seed)
+        g = torch.Generator().manual_seed(seed)
+        mask = (torch.rand(Lc, generator=g) < 0.15).cuda()
+        cache.kvcache_compression = True
+        cache.keypatches_mask_chunk = mask
+        base = int(cache.get_prev_temporal_idx(0)) + 1 if reforge else past
+        pos = (base + torch.arange(Lc))[None].cuda()
+        ko, vo = cache.update(k, v, 0, {"query_states": q, "position_ids": pos, "rotary_emb": rot, "mrope_section": None})
+        assert ko.shape == (1, KVH, past + Lc, D) and torch.equal(ko[:, :, past:], k)
+        idx = cache.last_keep_indices.long()
+        assert idx.numel() == keep and (keep == 1 or bool((idx[1:] > idx[:-1]).all()))
+        qq, kk = q, k
+        if reforge:
+            cos, sin = rot(v, pos)
+            qq = op.unrotate(q, cos, sin, rot.attention_scaling, "cuda")
+            kk = op.unrotate(k, cos, sin, rot.attention_scaling, "cuda")
+        ref_hs = ref_head_scores_cuda(qq, kk)
+        _check_keep(cache.last_keep_indices, cache.last_head_scores.mean(0), ref_hs.mean(0), mask, keep)
+        assert torch.equal(cache.layers[0].values[:, :, past:], v[:, :, idx])
+        if reforge:
+            want_pos = pos[..., idx].clone()
+            want_pos[0] = op.reforge_temporal(want_pos[0], keep, Lc)
+            assert torch.equal(cache.position_cache[0][..., past:], want_pos)
+            cos, sin = rot(v, want_pos)
+            assert torch.equal(cache.layers[0].keys[:, :, past:], op.rotate(kk[:, :, idx], cos, sin))
+        else:
+            assert torch.equal(cache.layers[0].keys[:, :, past:], k[:, :, idx])
+        past += keep
