@@ -50,7 +50,7 @@ int64_t     rtk_launch_count(void);
 /* Adjacent-frame cosine distance; replaces visual_compression.py:98-106
  * (F.cosine_similarity on bf16 + `1 - sim.float()` + the leading row of ones), replaying ATen-CUDA's
  * bf16 rounding chain and fp32 reduction order bit for bit.
- *   x    bf16 [T, N, C] contiguous, 16-byte aligned, C % 8 == 0, 256 <= C <= 8160
+ *   x    bf16 [T, N, C] contiguous, 16-byte aligned, C % 8 == 0, 256 <= C <= 8192
  *   halo 0: dis is fp32 [T, N]; row 0 is 1.0, row t is 1 - cos(x[t-1], x[t])
  *        1: x[0] is the last frame owned by the previous rank; dis is fp32 [T-1, N], row j belongs to x[j+1]
  */

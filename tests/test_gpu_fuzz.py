@@ -1,0 +1,115 @@
+"""Randomised shapes for the three selection kernels against torch's own CUDA ops (bit-exact): many (T, N, t) / (L, keep)
+combinations with small value alphabets (heavy ties at the selection boundary), negative values, signed zeros, NaN."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _mods():
+    from retake import longvideo_cache as lc
+    from retake import visual_compression as vc
+    return vc, lc
+
+
+def _ref_dpselect_indices(dis, t, sync):
+    """visual_compression.py:108-169 with torch-CUDA ops"""
+    import torch.nn.functional as F
+    T = dis.shape[0]
+    rows = dis.mean(1)[None] if sync else dis.t().contiguous()
+    arg = F.max_pool1d_with_indices(rows[:, None, :], 3, 1, padding=1)[1][:, 0]
+    peak = arg == torch.arange(T, device=dis.device)[None]
+    keys = torch.where(peak, rows + 2, rows)
+    kept = torch.topk(keys, k=t, sorted=False, dim=1)[1].sort(dim=1)[0]
+    if sync:
+        idx = kept[0]
+        return idx, peak[0][idx][:, None].repeat(1, dis.shape[1]).flatten()
+    return kept.t(), peak.t().gather(0, kept.t()).flatten()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_dpselect_select_fuzz(seed):
+    vc, _ = _mods()
+    g = torch.Generator().manual_seed(1000 + seed)
+    for _ in range(8):
+        T = int(torch.randint(1, 300, (1,), generator=g))
+        N = int(torch.randint(1, 200, (1,), generator=g))
+        t = int(torch.randint(1, T + 1, (1,), generator=g))
+        levels = int(torch.randint(2, 40, (1,), generator=g))
+        dis = (torch.randint(0, levels, (T, N), generator=g).float() / levels).cuda()
+        dis[0] = 1.0
+        if seed % 2:
+            dis = dis - 0.25                                  # negative distances and both zeros
+            dis[dis == 0] = -0.0
+        for sync in (False, True):
+            idx, mask = vc.dpselect_select(dis, t, sync)
+            want_idx, want_mask = _ref_dpselect_indices(dis, t, sync)
+            assert torch.equal(idx.long(), want_idx), (T, N, t, sync)
+            assert torch.equal(mask, want_mask), (T, N, t, sync)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pivot_select_fuzz(seed):
+    _, lc = _mods()
+    g = torch.Generator().manual_seed(2000 + seed)
+    for _ in range(10):
+        L = int(torch.randint(1, 5000, (1,), generator=g))
+        KVH = int(torch.randint(1, 9, (1,), generator=g))
+        keep = int(torch.randint(1, L + 1, (1,), generator=g))
+        levels = int(torch.randint(2, 50, (1,), generator=g))
+        hs = (torch.randint(0, levels, (KVH, L), generator=g).float() / 32 - (0.5 if seed % 2 else 0.0)).to(BF).cuda()
+        if seed == 5 and L > 4:
+            hs[0, 3] = float("nan")                           # NaN sorts first in ATen's radix order
+        mask = (torch.rand(L, generator=g) < 0.3).cuda() if seed % 3 else None
+        idx, score = lc.pivot_select(hs, keep, mask, return_scores=True)
+        s = hs.mean(0)
+        assert torch.equal(score.view(torch.int16), s.view(torch.int16))
+        if mask is not None:
+            s = s.masked_fill(mask, 1.0)
+        want = s.topk(keep).indices.sort().values
+        assert torch.equal(idx.long(), want), (L, KVH, keep)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_mallm_fuzz(seed):
+    """random small banks with repeated frames (equal similarities): fused loop == the reference's op loop on the GPU"""
+    from oracle import reference_ops as ro
+    vc, _ = _mods()
+    g = torch.Generator().manual_seed(3000 + seed)
+    for _ in range(4):
+        T = int(torch.randint(2, 40, (1,), generator=g))
+        N = int(torch.randint(1, 300, (1,), generator=g))
+        C = 256 + 8 * int(torch.randint(0, 64, (1,), generator=g))
+        t = int(torch.randint(1, T + 1, (1,), generator=g))
+        base = torch.randn(max(2, T // 3), N, C, generator=g)
+        x = base[torch.randint(0, base.shape[0], (T,), generator=g)].to(BF)[None].cuda()       # many identical frames
+        for sync in (False, True):
+            for hard in (False, True):
+                want, want_size = ro.mallm_compress(x.clone(), t, sync, hard)
+                got, got_size = vc.mallm_compress(x, t, sync=sync, hard=hard)
+                assert torch.equal(got, want), (T, N, C, t, sync, hard)
+                assert hard or torch.equal(got_size, want_size), (T, N, C, t, sync, hard)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_distance_fuzz_over_hidden_sizes(seed):
+    """every template instantiation of the streaming cosine kernel (K4 buckets, exact-multiple and ragged rows), random C"""
+    import torch.nn.functional as F
+    vc, _ = _mods()
+    g = torch.Generator().manual_seed(4000 + seed)
+    fixed = [256, 512, 1152, 2048, 3584, 4096, 6144, 8192, 264, 1160, 3592, 7680, 8184]
+    for i in range(8):
+        C = fixed[(seed * 5 + i) % len(fixed)] if i < 5 else 256 + 8 * int(torch.randint(0, 993, (1,), generator=g))
+        T = int(torch.randint(2, 24, (1,), generator=g))
+        N = int(torch.randint(1, 40, (1,), generator=g))
+        x = torch.randn(T, N, C, generator=g).to(BF)
+        x[T // 2] = x[T // 2 - 1]                             # an exactly repeated frame: sim == 1, dis == 0
+        x = x.cuda()
+        got = vc.dpselect_distance(x)
+        sim = F.cosine_similarity(x[:-1], x[1:], dim=-1)
+        want = torch.cat([torch.ones_like(sim[:1], dtype=torch.float32), 1 - sim.float()], dim=0)
+        assert torch.equal(got, want), (T, N, C)
+        if T > 2:
+            halo = vc.dpselect_distance(x[1:], halo=True)     # frames 2.. of the same video, frame 1 as halo
+            assert torch.equal(halo, want[2:]), (T, N, C)

@@ -54,14 +54,14 @@ struct RowCursor {
 template <int K4, bool AUX, bool EXACT>   // EXACT: C == K4 * 128, every lane owns K4 full vectors (no bounds checks)
 __global__ void __launch_bounds__(kDisThreads, (K4 <= 16) ? 2 : 1)
 dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis, int T, int N, int C, int R,
-                    int n_items, int stages, int halo, DisAux aux) {
+                    int n_items, int stages, int halo, DisAux aux, int active) {
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t row_bytes = (uint32_t)C * 2u;
     const int nv4 = C >> 2;                                  // 4-element vectors per row
     uint8_t* ring = smem + (size_t)warp * stages * row_bytes;
     const uint32_t ring_u32 = smem_u32(ring);
-    const uint32_t bars = smem_u32(smem + (size_t)kDisWarps * stages * row_bytes) + (uint32_t)(warp * stages) * 8u;
+    const uint32_t bars = smem_u32(smem + (size_t)active * stages * row_bytes) + (uint32_t)(warp * stages) * 8u;
 
     if (lane == 0) {
         for (int s = 0; s < stages; ++s) mbar_init(bars + 8u * s, 1);
@@ -69,8 +69,11 @@ dpselect_dis_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ dis
     }
     __syncthreads();
 
-    const int gw = blockIdx.x * kDisWarps + warp;
-    const int GW = gridDim.x * kDisWarps;
+    // rows longer than 7 KB leave room for fewer than two ring stages per warp with eight warps: then only `active`
+    // warps of the CTA stream rows (the rest idle after the barrier above)
+    if (warp >= active) return;
+    const int gw = blockIdx.x * active + warp;
+    const int GW = gridDim.x * active;
     RowCursor cons, prod;
     cons.init(gw, GW, n_items, N, R, T);
     prod = cons;
@@ -183,26 +186,31 @@ static int launch_dis(const void* x, int T, int N, int C, int halo, float* dis, 
     cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
     const size_t row_bytes = (size_t)C * 2;
     const int ctas_per_sm = (K4 <= 16) ? 2 : 1;
-    int stages = (int)(((size_t)smem_max / ctas_per_sm - 2048) / (kDisWarps * row_bytes));
+    int active = kDisWarps;
+    int stages = (int)(((size_t)smem_max / ctas_per_sm - 2048) / (active * row_bytes));
+    while (stages < 2 && active > 2) {                         // very long rows: fewer streaming warps, deeper rings
+        active >>= 1;
+        stages = (int)(((size_t)smem_max / ctas_per_sm - 2048) / (active * row_bytes));
+    }
     if (stages > 8) stages = 8;
     if (stages < 2) return RTK_E_UNSUPPORTED;
-    const size_t smem = (size_t)kDisWarps * stages * row_bytes + (size_t)kDisWarps * stages * 8;
+    const size_t smem = (size_t)active * stages * row_bytes + (size_t)kDisWarps * stages * 8;
     // run length: long enough that the halo re-read is small, short enough to give every warp >= 4 items
     const long long frames = T - 1;
-    const long long warps = (long long)sms * kDisWarps * ctas_per_sm;
+    const long long warps = (long long)sms * active * ctas_per_sm;
     long long R = (frames * N) / (warps * 4);
     if (R > 32) R = 32;
     if (R < 4) R = 4;
     if (R > frames) R = frames;
     const long long runs = (frames + R - 1) / R;
     const long long n_items = runs * N;
-    long long grid = (n_items + kDisWarps - 1) / kDisWarps;
+    long long grid = (n_items + active - 1) / active;
     if (grid > (long long)sms * ctas_per_sm) grid = (long long)sms * ctas_per_sm;
     auto kern = (!AUX && C == K4 * 128) ? dpselect_dis_kernel<K4, AUX, !AUX> : dpselect_dis_kernel<K4, AUX, false>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     kern<<<(unsigned)grid, kDisThreads, smem, st>>>((const __nv_bfloat16*)x, dis, T, N, C, (int)R, (int)n_items,
-                                                     stages, halo, aux);
+                                                     stages, halo, aux, active);
     RTK_CHECK_LAUNCH();
     return 0;
 }
@@ -457,7 +465,7 @@ using namespace rtk;
 
 extern "C" int rtk_dpselect_dis(const void* x, int64_t T, int64_t N, int64_t C, int halo, float* dis, void* stream) {
     if (!x || !dis || T < 1 || N < 1) return RTK_E_BADARG;
-    if (C % 8 != 0 || C < 256 || C > 8160) return RTK_E_UNSUPPORTED;
+    if (C % 8 != 0 || C < 256 || C > 8192) return RTK_E_UNSUPPORTED;
     if (((uintptr_t)x & 15u) != 0) return RTK_E_ALIGN;
     if (T > (1 << 20) || N > (1 << 20) || T * N > (1ll << 31) - 1) return RTK_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;

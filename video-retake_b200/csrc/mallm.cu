@@ -730,7 +730,7 @@ extern "C" int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T
                                   void* stream_) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!x || !out || !workspace || T < 1 || N < 1 || t < 1 || t > T) return RTK_E_BADARG;
-    if (C % 8 != 0 || C < 256 || C > 8160 || T > 8192 || N > 65535) return RTK_E_UNSUPPORTED;
+    if (C % 8 != 0 || C < 256 || C > 8192 || T > 8192 || N > 65535) return RTK_E_UNSUPPORTED;
     if (((uintptr_t)x | (uintptr_t)out | (uintptr_t)workspace) & 15u) return RTK_E_ALIGN;
     const MallmLayout L = mallm_layout(T, N, C, hard);
     if (workspace_bytes < L.total) return RTK_E_WORKSPACE;
