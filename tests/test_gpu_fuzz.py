@@ -113,3 +113,68 @@ def test_distance_fuzz_over_hidden_sizes(seed):
         if T > 2:
             halo = vc.dpselect_distance(x[1:], halo=True)     # frames 2.. of the same video, frame 1 as halo
             assert torch.equal(halo, want[2:]), (T, N, C)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_pivot_update_fuzz(seed):
+    """random (H, KVH, L, D, ratio, reforge, mrope / 1-D, mask) through PivotKVCache.update: scores within 1 bf16 ulp of the
+    torch-CUDA op sequence (O(1) logits; see the note below for huge ones), kept set consistent, kept V / K / positions exact
+    (ragged L, L < 128, G in {1, 2, 4, 7})."""
+    from helpers import TableRotary
+    from oracle import pivotkv as op
+    from test_gpu_pivotkv import _cfg, _check_keep, _lc, qkv, ref_head_scores_cuda, ulp_diff
+    lc = _lc()
+    g = torch.Generator().manual_seed(5000 + seed)
+    for trial in range(5):
+        D = (64, 128)[int(torch.randint(0, 2, (1,), generator=g))]
+        KVH = (1, 2, 4, 8)[int(torch.randint(0, 4, (1,), generator=g))]
+        G = (1, 2, 4, 7)[int(torch.randint(0, 4, (1,), generator=g))]
+        H = KVH * G
+        L = int(torch.randint(1, 2600, (1,), generator=g))
+        ratio = float(torch.rand(1, generator=g)) * 0.9 + 0.05
+        reforge = bool(torch.randint(0, 2, (1,), generator=g))
+        use_mrope = bool(torch.randint(0, 2, (1,), generator=g))
+        mrope = ([8, 12, 12] if D == 64 else [16, 24, 24]) if use_mrope else None
+        rot = TableRotary(D, mrope=use_mrope)
+        rot.inv_freq = rot.inv_freq.cuda()
+        cache = lc.PivotKVCache(_cfg(H, KVH, D, 1, ratio, reforge))
+        alpha = (1.0, 2.0)[trial % 2]
+        q, k, v = qkv(H, KVH, L, D, alpha, seed=seed * 100 + trial)
+        mask = (torch.rand(L, generator=g) < 0.25).cuda() if trial % 2 else None
+        cache.kvcache_compression = True
+        cache.keypatches_mask_chunk = mask
+        ar = torch.arange(L)
+        pos = (torch.stack([5 + ar // 64, (ar % 64) // 8, ar % 8])[:, None] if use_mrope else (5 + ar)[None]).cuda()
+        tag = (H, KVH, L, D, round(ratio, 3), reforge, use_mrope)
+        ko, vo = cache.update(k, v, 0, {"query_states": q, "position_ids": pos.clone(), "rotary_emb": rot, "mrope_section": mrope})
+        keep = max(1, int(ratio * L))
+        idx = cache.last_keep_indices.long()
+        assert idx.numel() == keep and torch.equal(ko, k) and torch.equal(vo, v), tag
+        qq, kk = q, k
+        if reforge:
+            cos, sin = rot(v, pos)
+            c1 = op.select_mrope(cos, mrope) if use_mrope else cos
+            s1 = op.select_mrope(sin, mrope) if use_mrope else sin
+            qq = op.unrotate(q, c1, s1, rot.attention_scaling, "cuda")
+            kk = op.unrotate(k, c1, s1, rot.attention_scaling, "cuda")
+        ref_hs = ref_head_scores_cuda(qq, kk)
+        d = ulp_diff(cache.last_head_scores, ref_hs)
+        if alpha == 1.0:
+            assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.02, tag
+        else:
+            # logits of magnitude ~100 have a bf16 ulp of ~1: ONE logit that cuBLAS' fp32 accumulation order rounds the other
+            # way moves a softmax weight by several per cent (tests/probes/probe_ulp2.py: the kernel then agrees with exactly
+            # computed dot products) - rare entries may be 2-3 steps apart, the bulk stays within one
+            assert int(d.max()) <= 4 and float((d > 1).float().mean()) < 1e-3 and float((d > 0).float().mean()) < 0.02, tag
+        _check_keep(cache.last_keep_indices, cache.last_head_scores.mean(0), ref_hs.mean(0), mask, keep)
+        assert torch.equal(cache.layers[0].values, v[:, :, idx]), tag
+        if not reforge:
+            assert torch.equal(cache.layers[0].keys, k[:, :, idx]), tag
+        else:
+            want_pos = pos[..., idx].clone()
+            want_pos[0] = op.reforge_temporal(want_pos[0], keep, L)
+            assert torch.equal(cache.position_cache[0], want_pos), tag
+            cos, sin = rot(v, want_pos)
+            c2 = op.select_mrope(cos, mrope) if use_mrope else cos
+            s2 = op.select_mrope(sin, mrope) if use_mrope else sin
+            assert torch.equal(cache.layers[0].keys, op.rotate(kk[:, :, idx], c2, s2)), tag
