@@ -178,3 +178,54 @@ def test_pivot_update_fuzz(seed):
             c2 = op.select_mrope(cos, mrope) if use_mrope else cos
             s2 = op.select_mrope(sin, mrope) if use_mrope else sin
             assert torch.equal(cache.layers[0].keys, op.rotate(kk[:, :, idx], c2, s2)), tag
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_cache_state_machine_fuzz(seed):
+    """random interleavings of compressing / plain updates over two layers with ragged chunk lengths, long enough to grow
+    the preallocated buffers several times: the cache must always equal [past kept rows | ...] built from the kernel's own
+    kept indices, the returned tensors must equal [past | chunk] (deferred tail overwrite, buffer growth, key_cache views)."""
+    from helpers import TableRotary
+    from test_gpu_pivotkv import _cfg, _lc, qkv
+    lc = _lc()
+    g = torch.Generator().manual_seed(6000 + seed)
+    H, KVH, D, layers = 4, 2, 64, 2
+    ratio = (0.1, 0.3, 0.6, 0.9)[seed]
+    rot = TableRotary(D, mrope=False)
+    rot.inv_freq = rot.inv_freq.cuda()
+    cache = lc.PivotKVCache(_cfg(H, KVH, D, layers, ratio, False))
+    want_k = [torch.empty(1, KVH, 0, D, dtype=BF, device="cuda") for _ in range(layers)]
+    want_v = [torch.empty(1, KVH, 0, D, dtype=BF, device="cuda") for _ in range(layers)]
+    evicted = [0] * layers
+    for step in range(14):
+        compress = bool(torch.randint(0, 4, (1,), generator=g))            # 3 of 4 steps compress
+        L = int(torch.randint(1, 3000, (1,), generator=g)) if compress else int(torch.randint(1, 40, (1,), generator=g))
+        cache.kvcache_compression = compress
+        cache.keypatches_mask_chunk = ((torch.rand(L, generator=g) < 0.2).cuda() if (compress and step % 2) else None)
+        for layer in range(layers):
+            q, k, v = qkv(H, KVH, L, D, 1.0, seed=seed * 1000 + step * 10 + layer)
+            pos = (want_k[layer].shape[2] + torch.arange(L))[None].cuda()
+            kw = {"position_ids": pos}
+            if compress:
+                kw.update({"query_states": q, "rotary_emb": rot, "mrope_section": None})
+            ko, vo = cache.update(k, v, layer, kw)
+            assert torch.equal(ko, torch.cat([want_k[layer], k], dim=2)) and torch.equal(vo, torch.cat([want_v[layer], v], dim=2))
+            if compress:
+                idx = cache.last_keep_indices.long()
+                assert idx.numel() == max(1, int(ratio * L))
+                want_k[layer] = torch.cat([want_k[layer], k[:, :, idx]], dim=2)
+                want_v[layer] = torch.cat([want_v[layer], v[:, :, idx]], dim=2)
+                evicted[layer] += L - idx.numel()
+            else:
+                want_k[layer] = torch.cat([want_k[layer], k], dim=2)
+                want_v[layer] = torch.cat([want_v[layer], v], dim=2)
+        if step % 3 == 2:
+            cache.after_forward()
+        for layer in range(layers):
+            assert cache.get_seq_length(layer) == want_k[layer].shape[2]
+            if step % 2:
+                assert torch.equal(cache.layers[layer].keys, want_k[layer]) and torch.equal(cache.key_cache[layer], want_k[layer])
+                assert torch.equal(cache.layers[layer].values, want_v[layer])
+    for layer in range(layers):
+        assert torch.equal(cache.layers[layer].keys, want_k[layer]) and torch.equal(cache.layers[layer].values, want_v[layer])
+        assert cache.num_evicted_tokens[layer] == evicted[layer]
