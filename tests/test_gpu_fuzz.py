@@ -128,7 +128,7 @@ def test_pivot_update_fuzz(seed):
     for trial in range(5):
         D = (64, 128)[int(torch.randint(0, 2, (1,), generator=g))]
         KVH = (1, 2, 4, 8)[int(torch.randint(0, 4, (1,), generator=g))]
-        G = (1, 2, 4, 7)[int(torch.randint(0, 4, (1,), generator=g))]
+        G = (1, 2, 4, 6, 7, 8)[int(torch.randint(0, 6, (1,), generator=g))]
         H = KVH * G
         L = int(torch.randint(1, 2600, (1,), generator=g))
         ratio = float(torch.rand(1, generator=g)) * 0.9 + 0.05
