@@ -627,8 +627,18 @@ __global__ void __launch_bounds__(1024) mallm_sync_argmax_kernel(MallmParams P, 
         __syncthreads();
     }
     const float rcp = 1.0f / (float)N;
-    for (int i = warp; i < T; i += nw) {
-        if (!all && P.touched[i] != stamp) continue;
+    // rows whose mean has to be refreshed: all of them, or the (few) rows stamped by this round's merge kernels - the
+    // stamps are fetched by all threads at once and compacted into a task list, one warp per task
+    __shared__ int s_ntask;
+    int* tasks = pos + T;                                        // [T]
+    if (threadIdx.x == 0) s_ntask = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < T; i += blockDim.x)
+        if (all || P.touched[i] == stamp) tasks[atomicAdd(&s_ntask, 1)] = i;
+    __syncthreads();
+    const int ntask = s_ntask;
+    for (int k = warp; k < ntask; k += nw) {
+        const int i = tasks[k];
         const float* row = P.sim + (size_t)i * P.si;
         float v = -INFINITY;
         if (row[0] != -INFINITY) {                               // dead and last rows hold -inf in every patch
@@ -757,7 +767,7 @@ extern "C" int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T
     P.touched = reinterpret_cast<int*>(ws + L.touched);
     P.sync = sync ? 1 : 0;
     P.hard = hard ? 1 : 0;
-    const size_t scan_smem = (size_t)T * 4;
+    const size_t scan_smem = (size_t)T * 8;                     // positions + task list of the sync argmax kernel
     if (sync) {
         cudaError_t e = cudaFuncSetAttribute(mallm_sync_argmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scan_smem);
         if (e != cudaSuccess) return (int)e;
