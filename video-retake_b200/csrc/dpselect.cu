@@ -257,18 +257,20 @@ __device__ __forceinline__ bool is_peak(const float* d, int i, int T) {
     return l && r;
 }
 
-// sync == 0: CTA handles 8 consecutive patch columns, one warp each.
+// sync == 0: a CTA of W warps (W = blockDim.x / 32, a power of two <= 8) handles W consecutive patch columns, one warp
+// each; W is chosen by the host so that the grid covers the machine (few patches per CTA when N is small).
 __global__ void __launch_bounds__(kSelWarps * kWarp)
 dpselect_select_patch_kernel(const float* __restrict__ dis, int T, int N, int t, int32_t* __restrict__ idx,
                              uint8_t* __restrict__ mask) {
     extern __shared__ __align__(128) uint8_t smem[];
-    float* sd = reinterpret_cast<float*>(smem);               // [8][T] raw distances, then radix keys in place
-    uint8_t* spk = smem + (size_t)kSelWarps * T * 4;          // [8][T] peak flags
-    const int p0 = blockIdx.x * kSelWarps;
-    const int np = min(kSelWarps, N - p0);
-    {   // thread (tt0, j) walks frames tt0, tt0+32, ...; 8 independent loads in flight per thread
-        const int j = threadIdx.x & (kSelWarps - 1), tt0 = threadIdx.x / kSelWarps;
-        constexpr int kStep = kSelWarps * kWarp / kSelWarps;          // frames covered per sweep of the block
+    const int W = blockDim.x >> 5;
+    float* sd = reinterpret_cast<float*>(smem);               // [W][T] raw distances, then radix keys in place
+    uint8_t* spk = smem + (size_t)W * T * 4;                  // [W][T] peak flags
+    const int p0 = blockIdx.x * W;
+    const int np = min(W, N - p0);
+    {   // thread (tt0, j) walks frames tt0, tt0 + 32, ...; 8 independent loads in flight per thread
+        const int j = threadIdx.x & (W - 1), tt0 = threadIdx.x / W;
+        constexpr int kStep = kWarp;                                  // frames covered per sweep of the block
         if (j < np) {
             const float* src = dis + p0 + j;
             float* dst = sd + j * T;
@@ -499,12 +501,14 @@ extern "C" int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64
         if (e != cudaSuccess) return (int)e;
         dpselect_select_sync_kernel<<<1, kSyncWarps * kWarp, smem, st>>>(dis, (int)T, (int)N, (int)t, idx, mask);
     } else {
-        const size_t smem = (size_t)kSelWarps * T * 5;
+        int W = kSelWarps;                                      // patches per CTA: fewer when that still leaves >= ~2 CTAs per SM
+        while (W > 1 && (N + W - 1) / W < 296) W >>= 1;
+        const size_t smem = (size_t)W * T * 5;
         cudaError_t e = cudaFuncSetAttribute(dpselect_select_patch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+                                             (int)((size_t)kSelWarps * T * 5));
         if (e != cudaSuccess) return (int)e;
-        const unsigned grid = (unsigned)((N + kSelWarps - 1) / kSelWarps);
-        dpselect_select_patch_kernel<<<grid, kSelWarps * kWarp, smem, st>>>(dis, (int)T, (int)N, (int)t, idx, mask);
+        const unsigned grid = (unsigned)((N + W - 1) / W);
+        dpselect_select_patch_kernel<<<grid, W * kWarp, smem, st>>>(dis, (int)T, (int)N, (int)t, idx, mask);
     }
     RTK_CHECK_LAUNCH();
     return 0;
