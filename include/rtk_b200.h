@@ -70,6 +70,8 @@ int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64_t t, int s
 
 /* Stream compaction of the surviving rows; replaces visual_compression.py:138 / :173.
  *   out[j, p, :] = x[idx[j, p], p, :] (sync=0)   or   x[idx[j], p, :] (sync=1);  out bf16 [t, N, C]
+ *   idx must be strictly ascending along j (what rtk_dpselect_select writes); t == T is therefore the identity and is
+ *   served by one device-to-device copy.
  */
 int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t C, const int32_t* idx, int64_t t,
                         int sync, void* out, void* stream);

@@ -519,6 +519,14 @@ extern "C" int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t 
     if (!x || !idx || !out || T < 1 || N < 1 || C < 1 || t < 1) return RTK_E_BADARG;
     if (C % 8 != 0) return RTK_E_UNSUPPORTED;
     if ((((uintptr_t)x | (uintptr_t)out) & 15u) != 0) return RTK_E_ALIGN;
+    if (t > T) return RTK_E_BADARG;
+    if (t == T) {
+        // idx is strictly ascending per column (rtk_dpselect_select): keeping every frame is the identity, and the
+        // compaction is one device-to-device copy at copy-engine speed (the shipped recipe, compression_ratio 1.0)
+        cudaError_t e = cudaMemcpyAsync(out, x, (size_t)T * N * C * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+        ++::rtk::g_launches;
+        return e == cudaSuccess ? 0 : (int)e;
+    }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
