@@ -68,7 +68,9 @@ def parse():
     ap.add_argument("--visual-ratio", type=float, default=1.0)
     ap.add_argument("--kv-ratio", type=float, default=-1.0, help="-1: dynamic, 32000 / video tokens (shipped recipe)")
     ap.add_argument("--no-reforge", action="store_true")
-    ap.add_argument("--pool", type=int, default=16, help="distinct Q/K/V sets cycled through the layer-chunks")
+    ap.add_argument("--pool", type=int, default=28, help="distinct Q/K/V sets cycled through the layer-chunks")
+    ap.add_argument("--immediate", action="store_true",
+                    help="compress inside every update() (one rtk_pivot_update per layer) instead of one batched call per chunk")
     ap.add_argument("--layers", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -84,6 +86,7 @@ class Shape:
         self.H, self.KVH, self.D = 28, 4, 128
         self.layers = a.layers
         self.reforge = not a.no_reforge
+        self.deferred = not a.immediate      # compression of a chunk's layers batched at after_forward()
         if a.shape == "qwen2vl":
             self.T = a.frames // 2            # temporal_patch_size 2
             self.N, self.C = 256, 3584        # DPSelect runs on the LLM-side embeddings
@@ -128,7 +131,8 @@ def cache_config(s):
                                 num_key_value_heads=s.KVH)
     cfg.longvideo_kwargs = {"kvcache_compression": True,
                             "kvcache_compression_kwargs": {"compression_ratio": s.kv_ratio, "compression_method": "pivotkv",
-                                                           "pos_embed_reforge": s.reforge}}
+                                                           "pos_embed_reforge": s.reforge,
+                                                           "deferred_compression": s.deferred}}
     return cfg
 
 
@@ -159,8 +163,9 @@ class ScoreTimer:
     """CUDA-event pairs recorded by the library around a sample of the scoring launches (rtk_pivot_score inside
     rtk_pivot_update) in the timed region; the events live on the stream the kernels are launched on."""
 
-    def __init__(self, every=8):
+    def __init__(self, every=8, calls_per_pair=1):
         self.every, self.n, self.pairs, self.on = every, 0, [], False
+        self.calls_per_pair = calls_per_pair      # scoring calls between the two events (a batched flush scores every layer)
         self.dpselect = []
 
     def arm(self, cache):
@@ -174,7 +179,7 @@ class ScoreTimer:
         self.pairs.append((a, b))
 
     def mean_ms(self):
-        return sum(a.elapsed_time(b) for a, b in self.pairs) / max(1, len(self.pairs))
+        return sum(a.elapsed_time(b) for a, b in self.pairs) / max(1, len(self.pairs)) / self.calls_per_pair
 
 
 def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer=None):
@@ -202,12 +207,14 @@ def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer=None):
                 pos[0] += cache.get_prev_temporal_idx(layer) + 1
             else:
                 pos[0] += c * (s.L // s.tok_per_grid if s.mrope else s.L)
-            if timer is not None:
+            if timer is not None and not s.deferred:
                 timer.arm(cache)
             cache.update(k[j:j + 1, :Lc].transpose(1, 2), v[j:j + 1, :Lc].transpose(1, 2), layer,
                          {"query_states": q[j:j + 1, :Lc].transpose(1, 2), "position_ids": pos, "rotary_emb": rotary,
                           "mrope_section": s.mrope})
-    cache.after_forward()
+        if timer is not None and s.deferred:
+            timer.arm(cache)
+        cache.after_forward()                                # the chunk loop's hook (qwen2_vl.py:715-716)
     return cache.last_keep_indices, cache.get_seq_length(0)
 
 
@@ -284,6 +291,7 @@ def main():
                 f"D={s.D}, r_kv={s.kv_ratio:.4g} (keep {s.keep}), reforge={s.reforge}")
     config = {"workload": workload, "frames": s.frames, "visual_ratio": s.t / s.T, "kv_ratio": s.kv_ratio,
               "pos_embed_reforge": s.reforge, "qkv_pool": a.pool,
+              "deferred_compression": s.deferred,
               "l2_policy": f"inputs larger than L2 (X {2 * s.T * s.N * s.C / 1e9:.2f} GB; Q/K/V pool cycled, reuse distance > 126 MB)",
               "parallelism": f"dp{world} (one video per GPU, no data-path collective)"}
 
@@ -321,7 +329,7 @@ def main():
     from retake import _native
     from retake import longvideo_cache as lc
     from retake import visual_compression as vc
-    timer = ScoreTimer()
+    timer = ScoreTimer(every=2, calls_per_pair=s.layers) if s.deferred else ScoreTimer()
     rotary = make_rotary(dev, s.name)
     host = synth_host(s, a.pool, 1234 + rank)
     x, q, k, v = [h.to(dev, non_blocking=True) for h in host]
@@ -417,7 +425,9 @@ def main():
     score_ms = timer.mean_ms()
     flops = 2.0 * s.H * s.L * s.L * s.D
     achieved = flops / (score_ms * 1e-3) / 1e12 if score_ms > 0 else 0.0
-    roofline = {"kernel": "pivot_score_kernel<1> + pivot_score_kernel<2> (one rtk_pivot_score call)", "bound": "tensor",
+    roofline = {"kernel": ("pivot_score_kernel<1> + pivot_score_kernel<2> (the scoring of one layer; timed around the batched "
+                           f"scoring of a chunk's {s.layers} layers, divided by {s.layers})") if s.deferred else
+                          "pivot_score_kernel<1> + pivot_score_kernel<2> (one rtk_pivot_score call)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "achieved_executed": 2 * achieved, "frac_executed": 2 * achieved / peak_tf, "peak_source": peak_src,
                 "ms_per_call": score_ms, "calls_timed": len(timer.pairs),

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RTK_ABI_VERSION 1
+#define RTK_ABI_VERSION 2
 
 #define RTK_E_BADARG      (-1)  /* null pointer / non-positive size                         */
 #define RTK_E_ALIGN       (-2)  /* pointer or stride not 16-byte aligned                    */
@@ -194,12 +194,26 @@ typedef struct rtk_pivot_update_args {
     void* head_scores;                                          /* bf16 [KVH, L]                                    */
     void* workspace; size_t workspace_bytes;
     void* ev_score_begin; void* ev_score_end;                   /* optional cudaEvent_t pair recorded around the scoring   */
+    int64_t pos_out_stride;                                     /* row stride of pos_out in elements; 0 = keep (ABI 2)     */
 } rtk_pivot_update_args;
 
 size_t rtk_pivot_update_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D);
 /* With inv_freq the kept keys come back re-rotated; with cos/sin tables (opaque rotary callable) the caller
  * finishes with rotary_emb_fn(v_out, pos_out) + rtk_pivot_rope(forward=1). */
 int rtk_pivot_update(const rtk_pivot_update_args* args, void* stream);
+
+/* The compressing updates of ALL layers of one chunk in one chain of seven launches (deferred compression: the
+ * reference's chunk loop calls past_key_values.after_forward() once the chunk's forward is done, retake/qwen2_vl.py:715-716,
+ * and a chunk's kept rows are first needed by the NEXT chunk - SURVEY.md 8(f2)).  layers[i] describes layer i exactly as
+ * for rtk_pivot_update; H, KVH, L, D, keep, reforge, n_pos, mrope_section and the rotary (inv_freq, attention_scaling)
+ * must be the same for every layer, reforge needs inv_freq (RTK_E_UNSUPPORTED otherwise: use rtk_pivot_update), pointers
+ * and strides are per layer; k_out / v_out may point straight into the layer's cache (rows D apart, heads out_stride_h
+ * apart) and pos_out into its position cache (rows pos_out_stride apart).  layers[i].workspace is ignored; `workspace`
+ * (256-byte aligned) holds the un-rotated Q / K copies and the row statistics of min(n_layers, 32) layers - more layers
+ * run as consecutive groups of 32.  layers[0].ev_score_begin / _end are recorded around the first group's scoring. */
+size_t rtk_pivot_update_batch_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D, int64_t n_layers);
+int rtk_pivot_update_batch(const rtk_pivot_update_args* layers, int64_t n_layers, void* workspace, size_t workspace_bytes,
+                           void* stream);
 
 #ifdef __cplusplus
 }

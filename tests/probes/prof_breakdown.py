@@ -87,7 +87,7 @@ past_k = torch.randn(1, KVH, 16000, D, device=dev).to(torch.bfloat16)
 pk["cat_past16k_chunk"] = timeit(lambda: torch.cat([past_k, k], dim=-2))
 
 # whole update through the public API: device time and host enqueue time
-cfg = bench.cache_config(type("S", (), {"H": H, "D": D, "layers": 1, "KVH": KVH, "kv_ratio": 0.122, "reforge": True})())
+cfg = bench.cache_config(type("S", (), {"H": H, "D": D, "layers": 1, "KVH": KVH, "kv_ratio": 0.122, "reforge": True, "deferred": False})())
 
 
 def one_update(cache):

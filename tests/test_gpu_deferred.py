@@ -1,0 +1,186 @@
+"""GPU parity of deferred (batched) PivotKV compression - SURVEY.md 8(f2): ``update`` appends, ``after_forward()`` runs the
+compression of all layers of the chunk as ONE ``rtk_pivot_update_batch`` call that writes the kept rows in place.  What
+every reader of the cache sees must equal compression inside ``update`` (``longvideo_cache.py:217-323``): same kept
+indices, same K / V / position caches, same bookkeeping."""
+import pytest
+import torch
+
+from helpers import TableRotary
+from test_gpu_pivotkv import _cfg, _check_keep, qkv, ref_head_scores_cuda, ulp_diff
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def _lc():
+    from retake import longvideo_cache as lc
+    return lc
+
+
+def _positions(L, base, mrope, n_tok=256):
+    ar = torch.arange(L, device="cuda")
+    if mrope:
+        return torch.stack([base + ar // n_tok, (ar % n_tok) // 16, ar % 16])[:, None]
+    return (ar + base)[None]
+
+
+def _run(lc, deferred, H, KVH, L, D, layers, chunks, ratio, reforge, mrope, flush="after_forward", alpha=1.0, hf_rotary=False):
+    """drive a cache like the chunk loop does; returns per-chunk observations and the final cache"""
+    cfg = _cfg(H, KVH, D, layers, ratio, reforge)
+    cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"] = deferred
+    cache = lc.PivotKVCache(cfg)
+    assert cache.deferred_compression is deferred
+    if hf_rotary:
+        import bench
+        rot = bench.make_rotary(torch.device("cuda"))
+    else:
+        rot = TableRotary(D, mrope=bool(mrope))
+        rot.inv_freq = rot.inv_freq.cuda()
+    obs = []
+    for c in range(chunks):
+        Lc = L if c < chunks - 1 or chunks == 1 else max(1, L // 2 + 3)         # ragged last chunk
+        mask = (torch.rand(Lc, generator=torch.Generator().manual_seed(50 + c)) < 0.15).cuda()
+        cache.kvcache_compression = True
+        cache.keypatches_mask_chunk = mask
+        per_layer = []
+        for layer in range(layers):
+            q, k, v = qkv(H, KVH, Lc, D, alpha, seed=1000 * c + layer)
+            base = int(cache.get_prev_temporal_idx(layer)) + 1 if reforge else 100 * c
+            pos = _positions(Lc, base, mrope)
+            past = cache.get_seq_length(layer)
+            ko, vo = cache.update(k, v, layer, {"query_states": q, "position_ids": pos, "rotary_emb": rot,
+                                                "mrope_section": mrope})
+            # this step's attention sees [past | uncompressed chunk]
+            assert ko.shape == (1, KVH, past + Lc, D) and torch.equal(ko[:, :, past:], k) and torch.equal(vo[:, :, past:], v)
+            keep = max(1, int(ratio * Lc))
+            assert cache.get_seq_length(layer) == past + keep
+            per_layer.append((q, k, v, pos, mask, keep, past))
+        if flush == "after_forward":
+            cache.after_forward()
+            if deferred:
+                assert not cache._deferred and all(l._deferred_owner is None for l in cache.layers)
+        obs.append(per_layer)
+    cache.after_forward()
+    return cache, obs
+
+
+SHAPES = [  # H, KVH, L, D, layers, chunks, ratio, reforge, mrope
+    (4, 2, 256, 64, 2, 3, 0.5, True, [8, 12, 12]),
+    (4, 2, 256, 64, 3, 2, 0.25, False, None),
+    (8, 2, 200, 128, 2, 2, 0.3, True, None),
+    (28, 4, 1024, 128, 4, 2, 0.122, True, [16, 24, 24]),
+    (28, 4, 1024, 128, 3, 2, 0.5, False, [16, 24, 24]),
+]
+
+
+@pytest.mark.parametrize("H,KVH,L,D,layers,chunks,ratio,reforge,mrope", SHAPES)
+def test_deferred_equals_immediate(H, KVH, L, D, layers, chunks, ratio, reforge, mrope):
+    lc = _lc()
+    a, _ = _run(lc, False, H, KVH, L, D, layers, chunks, ratio, reforge, mrope)
+    b, obs = _run(lc, True, H, KVH, L, D, layers, chunks, ratio, reforge, mrope)
+    assert a.num_evicted_tokens == b.num_evicted_tokens
+    for layer in range(layers):
+        assert a.get_seq_length(layer) == b.get_seq_length(layer)
+        ka, kb = a.layers[layer].keys, b.layers[layer].keys
+        assert ka.shape == kb.shape
+        assert torch.equal(a.layers[layer].values, b.layers[layer].values)
+        assert torch.equal(ka, kb)
+        if reforge:
+            assert torch.equal(a.position_cache[layer], b.position_cache[layer])
+    # the last chunk's exposed per-layer results
+    assert torch.equal(a.last_keep_indices, b.last_keep_indices)
+    # a CTA takes the same tile range of every layer as in a single-layer launch: the fp32 partials fold in the same order
+    assert torch.equal(a.last_head_scores, b.last_head_scores)
+
+
+def test_deferred_against_reference_scores():
+    """kept rows of every layer against the reference's op sequence on the GPU (no re-forging: K rows are plain gathers)"""
+    lc = _lc()
+    H, KVH, L, D, layers, ratio = 28, 4, 1024, 128, 5, 0.25
+    cfg = _cfg(H, KVH, D, layers, ratio, False)
+    cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"] = True
+    cache = lc.PivotKVCache(cfg)
+    mask = (torch.rand(L, generator=torch.Generator().manual_seed(3)) < 0.2).cuda()
+    cache.keypatches_mask_chunk = mask
+    pos = _positions(L, 0, None)
+    data, entries = [], []
+    for layer in range(layers):
+        q, k, v = qkv(H, KVH, L, D, 3.0, seed=layer)
+        cache.update(k, v, layer, {"query_states": q, "position_ids": pos})
+        data.append((q, k, v))
+        entries.append(cache._deferred[-1]["outs"])
+    assert len(cache._deferred) == layers
+    n0 = __import__("retake._native", fromlist=["x"]).launch_count()
+    cache.after_forward()
+    assert __import__("retake._native", fromlist=["x"]).launch_count() - n0 == 6       # one chain for all layers (no un-rotation)
+    keep = int(ratio * L)
+    for layer, ((q, k, v), outs) in enumerate(zip(data, entries)):
+        ref = ref_head_scores_cuda(q, k)
+        d = ulp_diff(outs["head_scores"], ref)
+        assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 0.02
+        _check_keep(outs["keep_idx"], outs["head_scores"].mean(0), ref.mean(0), mask, keep)
+        idx = outs["keep_idx"].long()
+        assert torch.equal(cache.layers[layer].keys, k[:, :, idx]) and torch.equal(cache.layers[layer].values, v[:, :, idx])
+
+
+def test_deferred_settles_without_after_forward():
+    """a caller that never calls after_forward(): the next update of a layer (or any read) settles the debt first"""
+    lc = _lc()
+    args = (4, 2, 256, 64, 2, 3, 0.5, True, [8, 12, 12])
+    a, _ = _run(lc, False, *args, flush="never")
+    b, _ = _run(lc, True, *args, flush="never")
+    for layer in range(2):
+        assert torch.equal(a.layers[layer].keys, b.layers[layer].keys)
+        assert torch.equal(a.layers[layer].values, b.layers[layer].values)
+        assert torch.equal(a.position_cache[layer], b.position_cache[layer])
+    # reads settle too
+    cfg = _cfg(4, 2, 64, 1, 0.5, False)
+    cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"] = True
+    c = lc.PivotKVCache(cfg)
+    q, k, v = qkv(4, 2, 128, 64, 1.0, seed=9)
+    c.update(k, v, 0, {"query_states": q, "position_ids": _positions(128, 0, None)})
+    assert len(c._deferred) == 1
+    keys = c.key_cache[0]
+    assert not c._deferred and keys.shape[2] == 64
+    assert torch.equal(keys, k[:, :, c.last_keep_indices.long()])
+
+
+def test_deferred_many_layers_and_hf_rotary():
+    """28 layers (the 7B depth) in one batch with the stock HF rotary module, and 35 layers (two groups of <= 32)"""
+    lc = _lc()
+    a, _ = _run(lc, False, 28, 4, 512, 128, 28, 2, 0.25, True, [16, 24, 24], hf_rotary=True)
+    b, _ = _run(lc, True, 28, 4, 512, 128, 28, 2, 0.25, True, [16, 24, 24], hf_rotary=True)
+    for layer in range(28):
+        assert torch.equal(a.layers[layer].keys, b.layers[layer].keys)
+        assert torch.equal(a.layers[layer].values, b.layers[layer].values)
+        assert torch.equal(a.position_cache[layer], b.position_cache[layer])
+    a, _ = _run(lc, False, 4, 2, 130, 64, 35, 1, 0.5, True, [8, 12, 12])
+    b, _ = _run(lc, True, 4, 2, 130, 64, 35, 1, 0.5, True, [8, 12, 12])
+    for layer in range(35):
+        assert torch.equal(a.layers[layer].keys, b.layers[layer].keys)
+        assert torch.equal(a.position_cache[layer], b.position_cache[layer])
+
+
+def test_deferred_full_size_chunk():
+    """7B shape, L = 4096, keep 500 (the benchmark's update), four layers"""
+    lc = _lc()
+    args = (28, 4, 4096, 128, 4, 2, 500 / 4096, True, [16, 24, 24])
+    a, _ = _run(lc, False, *args, hf_rotary=True)
+    b, _ = _run(lc, True, *args, hf_rotary=True)
+    for layer in range(4):
+        assert a.get_seq_length(layer) == b.get_seq_length(layer)
+        assert torch.equal(a.layers[layer].values, b.layers[layer].values)
+        assert torch.equal(a.layers[layer].keys, b.layers[layer].keys)
+        assert torch.equal(a.position_cache[layer], b.position_cache[layer])
+
+
+def test_deferred_opaque_rotary_falls_back_to_immediate(monkeypatch):
+    """an opaque rotary callable (tables must come from calling it) cannot be batched: update compresses right away"""
+    lc = _lc()
+    monkeypatch.setenv("RTK_ROTARY_TABLES", "1")
+    b, _ = _run(lc, True, 4, 2, 256, 64, 2, 2, 0.5, True, [8, 12, 12])
+    monkeypatch.setenv("RTK_ROTARY_TABLES", "0")
+    a, _ = _run(lc, False, 4, 2, 256, 64, 2, 2, 0.5, True, [8, 12, 12])
+    for layer in range(2):
+        assert torch.equal(a.layers[layer].keys, b.layers[layer].keys)
+        assert torch.equal(a.position_cache[layer], b.position_cache[layer])

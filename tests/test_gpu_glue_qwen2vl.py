@@ -38,13 +38,14 @@ def make_inputs(T=16, H=8, W=8, pre=5, post=6):
                 video_grid_thw=torch.tensor([[T, H, W]]).cuda(), attention_mask=torch.ones(1, ids.numel(), dtype=torch.long).cuda())
 
 
-def lv_kwargs(rv=1.0, rkv=1.0, reforge=False, chunk_frames=8, kv=True):
+def lv_kwargs(rv=1.0, rkv=1.0, reforge=False, chunk_frames=8, kv=True, deferred=False):
     return {"frame_chunk_size": 8, "chunked_prefill_frames": chunk_frames, "visual_compression": True,
             "visual_compression_kwargs": {"compression_ratio": rv, "compression_method": "Keyframe", "patch_sync": False,
                                           "return_keyframe_mask": True},
             "kvcache_compression": kv,
             "kvcache_compression_kwargs": {"dynamic_compression_ratio": False, "compression_ratio": rkv,
-                                           "compression_method": "pivotkv", "pos_embed_reforge": reforge}}
+                                           "compression_method": "pivotkv", "pos_embed_reforge": reforge,
+                                           "deferred_compression": deferred}}
 
 
 @pytest.fixture()
@@ -102,12 +103,32 @@ def test_chunked_prefill_without_compression_equals_one_shot(patched):
     assert torch.allclose(a, ref_logits, atol=0.08, rtol=0.05), float((a - ref_logits).abs().max())
 
 
+def test_deferred_compression_gives_the_same_prefill(patched):
+    """deferred_compression: the chunk loop's after_forward() runs ONE batched compression per chunk; logits and caches
+    equal compression inside update() bit for bit"""
+    model = tiny_model()
+    inp = make_inputs()
+    outs = []
+    for deferred in (False, True):
+        model.config.longvideo_kwargs = lv_kwargs(rv=0.5, rkv=0.5, reforge=True, chunk_frames=8, deferred=deferred)
+        with torch.no_grad():
+            outs.append(model(**inp, use_cache=True))
+    a, b = outs
+    assert b.past_key_values.deferred_compression and not a.past_key_values.deferred_compression
+    assert torch.equal(a.logits, b.logits)
+    for l in range(2):
+        assert torch.equal(a.past_key_values.layers[l].keys, b.past_key_values.layers[l].keys)
+        assert torch.equal(a.past_key_values.layers[l].values, b.past_key_values.layers[l].values)
+        assert torch.equal(a.past_key_values.position_cache[l], b.past_key_values.position_cache[l])
+
+
+@pytest.mark.parametrize("deferred", [False, True])
 @pytest.mark.parametrize("reforge", [False, True])
-def test_compressed_prefill_and_generate(patched, reforge):
+def test_compressed_prefill_and_generate(patched, reforge, deferred):
     from retake.longvideo_cache import PivotKVCache
     model = tiny_model()
     inp = make_inputs()
-    model.config.longvideo_kwargs = lv_kwargs(rv=0.5, rkv=0.5, reforge=reforge, chunk_frames=8)
+    model.config.longvideo_kwargs = lv_kwargs(rv=0.5, rkv=0.5, reforge=reforge, chunk_frames=8, deferred=deferred)
     with torch.no_grad():
         o = model(**inp, use_cache=True)
     cache = o.past_key_values

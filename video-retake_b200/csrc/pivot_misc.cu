@@ -78,10 +78,9 @@ __device__ __forceinline__ void rope_table_entry(const RopeParams& p, const floa
 // Reverse rotation of q and k with the tables computed in place (fast path: the rotary module has a static inv_freq):
 // one CTA per token, D threads build the token's cos/sin row in shared memory, then every thread rotates one
 // (head, 8+8 channel) slice of q or k.  Replaces pivot_rope_table_kernel + pivot_rope_kernel of the slow path.
-__global__ void __launch_bounds__(256)
-pivot_unrope_qk_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ pos, const float* __restrict__ inv_freq,
-                       float scaling, __nv_bfloat16* __restrict__ out, RopeParams p) {
-    pdl_enter();
+__device__ __forceinline__ void unrope_qk_body(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ pos,
+                                               const float* __restrict__ inv_freq, float scaling,
+                                               __nv_bfloat16* __restrict__ out, const RopeParams& p) {
     __shared__ float s_cos[256], s_sin[256];
     const int half = p.D >> 1;
     const int vec_per_row = half >> 3;
@@ -116,6 +115,47 @@ pivot_unrope_qk_kernel(const __nv_bfloat16* __restrict__ x, const long long* __r
         }
         __syncthreads();
     }
+}
+
+__global__ void __launch_bounds__(256)
+pivot_unrope_qk_kernel(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ pos, const float* __restrict__ inv_freq,
+                       float scaling, __nv_bfloat16* __restrict__ out, RopeParams p) {
+    pdl_enter();
+    unrope_qk_body(x, pos, inv_freq, scaling, out, p);
+}
+
+// Per-layer tables of a batched update (rtk_pivot_update_batch): every layer of the chunk brings its own tensors, the
+// shapes are shared.  Passed as ONE __grid_constant__ kernel parameter (4.9 KB).
+struct BatchLayers {
+    const __nv_bfloat16* q[kMaxBatchLayers];         // caller's views (un-rotation input)
+    const __nv_bfloat16* k[kMaxBatchLayers];         // K the compaction reads (the un-rotated copy when re-forging)
+    const __nv_bfloat16* k_in[kMaxBatchLayers];      // caller's K view (un-rotation input)
+    const __nv_bfloat16* v[kMaxBatchLayers];
+    __nv_bfloat16* qu[kMaxBatchLayers];              // un-rotated copies [H, L, D] / [KVH, L, D] in the workspace
+    __nv_bfloat16* ku[kMaxBatchLayers];
+    const long long* pos[kMaxBatchLayers];
+    const uint8_t* keymask[kMaxBatchLayers];
+    __nv_bfloat16* k_out[kMaxBatchLayers];
+    __nv_bfloat16* v_out[kMaxBatchLayers];
+    long long* pos_out[kMaxBatchLayers];
+    int32_t* keep_idx[kMaxBatchLayers];
+    const __nv_bfloat16* head_scores[kMaxBatchLayers];
+    long long q_stride_h[kMaxBatchLayers], q_stride_l[kMaxBatchLayers];
+    long long kin_stride_h[kMaxBatchLayers], kin_stride_l[kMaxBatchLayers];
+    long long k_stride_h[kMaxBatchLayers], k_stride_l[kMaxBatchLayers];
+    long long v_stride_h[kMaxBatchLayers], v_stride_l[kMaxBatchLayers];
+    long long out_stride_h[kMaxBatchLayers], pos_out_stride[kMaxBatchLayers];
+};
+
+// grid (L, layers): the un-rotation of q and k of every layer of the chunk in one launch
+__global__ void __launch_bounds__(256)
+pivot_unrope_qk_batch_kernel(const __grid_constant__ BatchLayers t, const float* __restrict__ inv_freq, float scaling, RopeParams p) {
+    pdl_enter();
+    const int layer = blockIdx.y;
+    p.stride_h = t.q_stride_h[layer]; p.stride_l = t.q_stride_l[layer];
+    p.x2 = t.k_in[layer]; p.out2 = t.ku[layer];
+    p.stride_h2 = t.kin_stride_h[layer]; p.stride_l2 = t.kin_stride_l[layer];
+    unrope_qk_body(t.q[layer], t.pos[layer], inv_freq, scaling, t.qu[layer], p);
 }
 
 // one thread: 8 channels of the lower half and the 8 partner channels of the upper half of one (head, token)
@@ -244,11 +284,10 @@ __device__ void block_select_top(const uint32_t* keys, int L, int keep, int32_t*
     }
 }
 
-__global__ void __launch_bounds__(kSelThreads)
-pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int L, const uint8_t* __restrict__ keymask,
-                    int keep, int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ score_out,
-                    const long long* __restrict__ tpos, long long* __restrict__ tmin_out) {
-    pdl_enter();
+__device__ __forceinline__ void pivot_select_body(const __nv_bfloat16* __restrict__ head_scores, int KVH, int L,
+                                                  const uint8_t* __restrict__ keymask, int keep, int32_t* __restrict__ keep_idx,
+                                                  __nv_bfloat16* __restrict__ score_out, const long long* __restrict__ tpos,
+                                                  long long* __restrict__ tmin_out) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint32_t* keys = reinterpret_cast<uint32_t*>(smem);        // [L]
     int* sh = reinterpret_cast<int*>(smem + (size_t)L * 4);    // scratch
@@ -281,12 +320,30 @@ pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int 
     }
 }
 
+__global__ void __launch_bounds__(kSelThreads)
+pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int L, const uint8_t* __restrict__ keymask,
+                    int keep, int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ score_out,
+                    const long long* __restrict__ tpos, long long* __restrict__ tmin_out) {
+    pdl_enter();
+    pivot_select_body(head_scores, KVH, L, keymask, keep, keep_idx, score_out, tpos, tmin_out);
+}
+
+// one CTA per layer of the chunk
+__global__ void __launch_bounds__(kSelThreads)
+pivot_select_batch_kernel(const __grid_constant__ BatchLayers t, int KVH, int L, int keep, int reforge, long long* __restrict__ tmin) {
+    pdl_enter();
+    const int layer = blockIdx.x;
+    pivot_select_body(t.head_scores[layer], KVH, L, t.keymask[layer], keep, t.keep_idx[layer], nullptr,
+                      reforge ? t.pos[layer] : nullptr, reforge ? tmin + layer : nullptr);
+}
+
 // ======================================================================================= B3: compaction
 // grid.x blocks gather KV rows (one 16-byte vector per thread-iteration); the LAST block handles positions.
 struct CompactParams {
     int KVH, L, D, keep, n_pos, reforge;
     long long stride_h, stride_l, out_stride_h;
     long long v_stride_h, v_stride_l;
+    long long pos_out_stride; // row stride of pos_out (= keep for a standalone [n_pos, keep] tensor)
     float ratio;              // fp32(keep / L)
 };
 
@@ -338,13 +395,12 @@ pivot_compact_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* _
 // Fused tail of an update (fast path): one CTA per kept token gathers its K and V rows of every KV head, writes its
 // (re-indexed) position ids and - when re-forging - rotates K to the new position with the cos/sin row built in place.
 // Replaces pivot_compact_kernel + pivot_rope_table_kernel + pivot_rope_kernel (longvideo_cache.py:278-306).
-__global__ void __launch_bounds__(128)
-pivot_compact_rope_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
-                          const int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ k_out,
-                          __nv_bfloat16* __restrict__ v_out, const long long* __restrict__ pos, long long* __restrict__ pos_out,
-                          const long long* __restrict__ tmin, const float* __restrict__ inv_freq, float scaling, CompactParams p,
-                          RopeParams rp, int rotate) {
-    pdl_enter();
+__device__ __forceinline__ void compact_rope_body(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                                                  const int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ k_out,
+                                                  __nv_bfloat16* __restrict__ v_out, const long long* __restrict__ pos,
+                                                  long long* __restrict__ pos_out, const long long* __restrict__ tmin,
+                                                  const float* __restrict__ inv_freq, float scaling, const CompactParams& p,
+                                                  const RopeParams& rp, int rotate) {
     __shared__ float s_cos[256], s_sin[256];
     __shared__ long long s_pos[3];
     const int j = blockIdx.x, tid = threadIdx.x;
@@ -356,7 +412,7 @@ pivot_compact_rope_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat
             const long long mn = *tmin;
             pv = mn + (long long)((float)(pv - mn) * p.ratio);
         }
-        pos_out[(size_t)tid * p.keep + j] = pv;
+        pos_out[(size_t)tid * p.pos_out_stride + j] = pv;
         s_pos[tid] = pv;
     }
     const int vec_per_row = p.D >> 3;
@@ -393,6 +449,30 @@ pivot_compact_rope_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat
         *reinterpret_cast<uint4*>(dst + c0) = ol4;
         *reinterpret_cast<uint4*>(dst + c0 + half) = oh4;
     }
+}
+
+__global__ void __launch_bounds__(128)
+pivot_compact_rope_kernel(const __nv_bfloat16* __restrict__ k, const __nv_bfloat16* __restrict__ v,
+                          const int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ k_out,
+                          __nv_bfloat16* __restrict__ v_out, const long long* __restrict__ pos, long long* __restrict__ pos_out,
+                          const long long* __restrict__ tmin, const float* __restrict__ inv_freq, float scaling, CompactParams p,
+                          RopeParams rp, int rotate) {
+    pdl_enter();
+    compact_rope_body(k, v, keep_idx, k_out, v_out, pos, pos_out, tmin, inv_freq, scaling, p, rp, rotate);
+}
+
+// grid (keep, layers): kept rows of every layer of the chunk straight into their caches
+__global__ void __launch_bounds__(128)
+pivot_compact_rope_batch_kernel(const __grid_constant__ BatchLayers t, const long long* __restrict__ tmin,
+                                const float* __restrict__ inv_freq, float scaling, CompactParams p, RopeParams rp, int rotate) {
+    pdl_enter();
+    const int layer = blockIdx.y;
+    p.stride_h = t.k_stride_h[layer]; p.stride_l = t.k_stride_l[layer];
+    p.v_stride_h = t.v_stride_h[layer]; p.v_stride_l = t.v_stride_l[layer];
+    p.out_stride_h = t.out_stride_h[layer];
+    p.pos_out_stride = t.pos_out_stride[layer];
+    compact_rope_body(t.k[layer], t.v[layer], t.keep_idx[layer], t.k_out[layer], t.v_out[layer], t.pos[layer], t.pos_out[layer],
+                      tmin + layer, inv_freq, scaling, p, rp, rotate);
 }
 
 // up to four strided [heads, rows, D] block copies in ONE launch (cache append of K and V + the deferred overwrite of the
@@ -520,6 +600,7 @@ static int compact_kv(const void* k, const void* v, int64_t KVH, int64_t L, int6
     p.KVH = (int)KVH; p.L = (int)L; p.D = (int)D; p.keep = (int)keep; p.n_pos = n_pos; p.reforge = reforge;
     p.stride_h = stride_h; p.stride_l = stride_l; p.out_stride_h = out_stride_h;
     p.v_stride_h = v_stride_h; p.v_stride_l = v_stride_l;
+    p.pos_out_stride = keep;
     p.ratio = (float)((double)keep / (double)L);
     const long long total = KVH * keep * (D / 8);
     long long grid = (total + 255) / 256;
@@ -661,6 +742,7 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
         p.KVH = (int)KVH; p.L = (int)L; p.D = (int)D; p.keep = (int)a->keep; p.n_pos = a->pos ? a->n_pos : 0; p.reforge = a->reforge;
         p.stride_h = ksh; p.stride_l = ksl; p.out_stride_h = a->out_stride_h;
         p.v_stride_h = a->v_stride_h; p.v_stride_l = a->v_stride_l;
+        p.pos_out_stride = a->pos_out_stride > 0 ? a->pos_out_stride : a->keep;
         p.ratio = (float)((double)a->keep / (double)L);
         RopeParams rp = {};
         rp.D = (int)D; rp.n_pos = a->n_pos; rp.L = (int)a->keep;
@@ -673,6 +755,121 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
                        (const __nv_bfloat16*)a->v, (const int32_t*)a->keep_idx, (__nv_bfloat16*)a->k_out, (__nv_bfloat16*)a->v_out,
                        (const long long*)a->pos, (long long*)a->pos_out, (const long long*)tmin, a->inv_freq, a->attention_scaling, p,
                        rp, fused_tables ? 1 : 0);
+    }
+    return 0;
+}
+
+extern "C" size_t rtk_pivot_update_batch_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D, int64_t n_layers) {
+    if (H < 1 || KVH < 1 || L < 1 || D < 1 || n_layers < 1) return 0;
+    const size_t n = (size_t)(n_layers < kMaxBatchLayers ? n_layers : kMaxBatchLayers);
+    return align256(rtk_pivot_score_workspace_bytes(H * (int64_t)n, L)) +
+           n * (align256((size_t)H * L * D * 2) + align256((size_t)KVH * L * D * 2)) + align256(n * sizeof(long long)) + 256;
+}
+
+// one group of <= kMaxBatchLayers layers
+static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, cudaStream_t st) {
+    const rtk_pivot_update_args& a0 = a[0];
+    const int64_t H = a0.H, KVH = a0.KVH, L = a0.L, D = a0.D;
+    const bool reforge = a0.reforge != 0;
+    void* score_ws = ws;                ws += align256(rtk_pivot_score_workspace_bytes(H * n, L));
+    char* qu0 = ws;                     ws += (size_t)n * align256((size_t)H * L * D * 2);
+    char* ku0 = ws;                     ws += (size_t)n * align256((size_t)KVH * L * D * 2);
+    long long* tmin = (long long*)ws;
+
+    BatchLayers t = {};
+    ScoreBatch sb = {};
+    sb.n = n; sb.H = H; sb.KVH = KVH; sb.L = L; sb.D = D;
+    for (int i = 0; i < kMaxBatchLayers; ++i) {
+        const rtk_pivot_update_args& x = a[i < n ? i : 0];       // unused slots repeat layer 0 (never dereferenced)
+        char* qu = qu0 + (size_t)(i < n ? i : 0) * align256((size_t)H * L * D * 2);
+        char* ku = ku0 + (size_t)(i < n ? i : 0) * align256((size_t)KVH * L * D * 2);
+        t.q[i] = (const __nv_bfloat16*)x.q;       t.q_stride_h[i] = x.q_stride_h;     t.q_stride_l[i] = x.q_stride_l;
+        t.k_in[i] = (const __nv_bfloat16*)x.k;    t.kin_stride_h[i] = x.k_stride_h;   t.kin_stride_l[i] = x.k_stride_l;
+        t.qu[i] = (__nv_bfloat16*)qu;             t.ku[i] = (__nv_bfloat16*)ku;
+        t.k[i] = reforge ? (const __nv_bfloat16*)ku : (const __nv_bfloat16*)x.k;
+        t.k_stride_h[i] = reforge ? L * D : x.k_stride_h;
+        t.k_stride_l[i] = reforge ? D : x.k_stride_l;
+        t.v[i] = (const __nv_bfloat16*)x.v;       t.v_stride_h[i] = x.v_stride_h;     t.v_stride_l[i] = x.v_stride_l;
+        t.pos[i] = (const long long*)x.pos;       t.keymask[i] = x.keymask;
+        t.k_out[i] = (__nv_bfloat16*)x.k_out;     t.v_out[i] = (__nv_bfloat16*)x.v_out;
+        t.out_stride_h[i] = x.out_stride_h;
+        t.pos_out[i] = (long long*)x.pos_out;     t.pos_out_stride[i] = x.pos_out_stride > 0 ? x.pos_out_stride : x.keep;
+        t.keep_idx[i] = x.keep_idx;               t.head_scores[i] = (const __nv_bfloat16*)x.head_scores;
+        if (i < n) {
+            sb.q[i] = reforge ? (const void*)qu : x.q;
+            sb.k[i] = reforge ? (const void*)ku : x.k;
+            sb.q_stride_h[i] = reforge ? L * D : x.q_stride_h;   sb.q_stride_l[i] = reforge ? D : x.q_stride_l;
+            sb.k_stride_h[i] = reforge ? L * D : x.k_stride_h;   sb.k_stride_l[i] = reforge ? D : x.k_stride_l;
+            sb.head_scores[i] = x.head_scores;
+        }
+    }
+    RopeParams rp = {};
+    rp.heads = (int)H; rp.L = (int)L; rp.D = (int)D; rp.n_pos = a0.n_pos; rp.forward = 0;
+    rp.out_stride_h = L * D; rp.out_stride_l = D;
+    rp.heads2 = (int)KVH; rp.out_stride_h2 = L * D; rp.out_stride_l2 = D;
+    rp.inv_scale2 = a0.inv_scale2;
+    int acc = 0;
+    for (int i = 0; i < 6; ++i) {
+        acc += (a0.n_pos == 3) ? a0.mrope_section[i % 3] : 0;
+        rp.bound[i] = acc;
+    }
+    if (reforge) {
+        if (a0.n_pos == 3 && acc != D) return RTK_E_UNSUPPORTED;
+        RTK_LAUNCH_PDL(pivot_unrope_qk_batch_kernel, dim3((unsigned)L, (unsigned)n), 256, 0, st, t, a0.inv_freq,
+                       a0.attention_scaling, rp);
+    }
+    if (a0.ev_score_begin) cudaEventRecord((cudaEvent_t)a0.ev_score_begin, st);
+    int rc = pivot_score_batch(sb, score_ws, rtk_pivot_score_workspace_bytes(H * n, L), st);
+    if (rc) return rc;
+    if (a0.ev_score_end) cudaEventRecord((cudaEvent_t)a0.ev_score_end, st);
+    {
+        const size_t smem = (size_t)L * 4 + 112 * 4;
+        cudaError_t e = cudaFuncSetAttribute(pivot_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+        RTK_LAUNCH_PDL(pivot_select_batch_kernel, (unsigned)n, kSelThreads, smem, st, t, (int)KVH, (int)L, (int)a0.keep,
+                       reforge ? 1 : 0, tmin);
+    }
+    {
+        CompactParams p = {};
+        p.KVH = (int)KVH; p.L = (int)L; p.D = (int)D; p.keep = (int)a0.keep; p.n_pos = a0.pos ? a0.n_pos : 0; p.reforge = a0.reforge;
+        p.ratio = (float)((double)a0.keep / (double)L);
+        RopeParams rq = {};
+        rq.D = (int)D; rq.n_pos = a0.n_pos; rq.L = (int)a0.keep;
+        for (int i = 0; i < 6; ++i) rq.bound[i] = rp.bound[i];
+        RTK_LAUNCH_PDL(pivot_compact_rope_batch_kernel, dim3((unsigned)a0.keep, (unsigned)n), 128, 0, st, t, (const long long*)tmin,
+                       a0.inv_freq, a0.attention_scaling, p, rq, reforge ? 1 : 0);
+    }
+    return 0;
+}
+
+extern "C" int rtk_pivot_update_batch(const rtk_pivot_update_args* layers, int64_t n_layers, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+    if (!layers || n_layers < 1 || !workspace) return RTK_E_BADARG;
+    const rtk_pivot_update_args& a0 = layers[0];
+    if (a0.H < 1 || a0.KVH < 1 || a0.L < 1 || a0.keep < 1 || a0.keep > a0.L) return RTK_E_BADARG;
+    if (a0.L > 16384 || a0.D % 16 != 0 || a0.D > 256 || a0.skip_select) return RTK_E_UNSUPPORTED;
+    if (a0.reforge && !a0.inv_freq) return RTK_E_UNSUPPORTED;        // opaque rotary callables go through rtk_pivot_update
+    if (((uintptr_t)workspace & 255u) != 0) return RTK_E_ALIGN;
+    if (workspace_bytes < rtk_pivot_update_batch_workspace_bytes(a0.H, a0.KVH, a0.L, a0.D, n_layers)) return RTK_E_WORKSPACE;
+    for (int64_t i = 0; i < n_layers; ++i) {
+        const rtk_pivot_update_args& x = layers[i];
+        if (!x.q || !x.k || !x.v || !x.k_out || !x.v_out || !x.keep_idx || !x.head_scores) return RTK_E_BADARG;
+        if (x.H != a0.H || x.KVH != a0.KVH || x.L != a0.L || x.D != a0.D || x.keep != a0.keep || x.reforge != a0.reforge ||
+            x.n_pos != a0.n_pos || x.inv_freq != a0.inv_freq || x.attention_scaling != a0.attention_scaling ||
+            x.inv_scale2 != a0.inv_scale2 || x.skip_select || (x.pos == nullptr) != (a0.pos == nullptr))
+            return RTK_E_UNSUPPORTED;                                 // one chunk: the layers share shape and rotary
+        for (int j = 0; j < 3; ++j)
+            if (x.mrope_section[j] != a0.mrope_section[j]) return RTK_E_UNSUPPORTED;
+        if (x.reforge && (!x.pos || !x.pos_out)) return RTK_E_BADARG;
+        if (x.pos && (!x.pos_out || x.n_pos < 1 || x.n_pos > 3)) return RTK_E_BADARG;
+        if ((((uintptr_t)x.q | (uintptr_t)x.k | (uintptr_t)x.v | (uintptr_t)x.k_out | (uintptr_t)x.v_out) & 15u) != 0) return RTK_E_ALIGN;
+        if ((x.q_stride_h | x.q_stride_l | x.k_stride_h | x.k_stride_l | x.v_stride_h | x.v_stride_l | x.out_stride_h) % 8 != 0)
+            return RTK_E_ALIGN;
+    }
+    for (int64_t i = 0; i < n_layers; i += kMaxBatchLayers) {
+        const int n = (int)((n_layers - i) < kMaxBatchLayers ? (n_layers - i) : kMaxBatchLayers);
+        const int rc = pivot_update_group(layers + i, n, (char*)workspace, (cudaStream_t)stream);
+        if (rc) return rc;
     }
     return 0;
 }

@@ -179,8 +179,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // D fp32, A/B bf16, both K-major, M = N = 128
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
+// Several layers of one chunk can be scored by the same pair of launches (rtk_pivot_update_batch): the unit space is
+// (layer, head, stationary tile) and every layer brings its own pair of tensor maps.
+template <int NL>
+struct ScoreMaps {
+    CUtensorMap q[NL], k[NL];
+};
+
 struct ScoreParams {
-    int H, G, L, nt;                  // heads, heads per KV group, chunk length, tiles = ceil(L / 128)
+    int H, G, L, nt;                  // heads of ALL layers in the launch, heads per KV group, chunk length, tiles = ceil(L / 128)
+    int Hl;                           // heads per layer (H = layers * Hl)
     int n_atoms;                      // D / 64
     int q_dim1_is_l, k_dim1_is_l;     // tensor-map coordinate order (dims are sorted by stride on the host)
     float inv_sqrt_d;                 // fp32(1 / fp32(sqrt D))
@@ -378,34 +386,47 @@ __device__ __forceinline__ void softmax_cols(uint32_t (&r)[NC], int col0, int va
     }
 }
 
-// One CTA's share of the flattened (unit, streamed tile) space: a contiguous range, so every SM gets the same
-// number of tile-steps (+-1) and a unit is shared by at most two CTAs (range length >= nt).
+// One CTA's share of the flattened (unit, streamed tile) space of a layer: a contiguous range, so every SM gets the same
+// number of tile-steps (+-1) and a unit is shared by at most two CTAs (range length >= nt).  With several layers in the
+// launch the CTA takes ITS range of every layer in turn - the cut points inside a layer are those of a single-layer
+// launch, so batched and per-layer scoring fold their fp32 partials in the same order and agree bit for bit.
 #ifndef RTK_SCORE_EVEN_RANGES
 #define RTK_SCORE_EVEN_RANGES 0     // 1: even-aligned tile ranges (A/B: no gain)
 #endif
 struct TileRange {
-    long long g, g1;
-    int nt;
-    __device__ __forceinline__ TileRange(int H, int nt_) : nt(nt_) {
-        const long long G = (long long)H * nt_ * nt_;
-        g = G * blockIdx.x / gridDim.x;
-        g1 = G * (blockIdx.x + 1) / gridDim.x;
+    long long g, g1, Gl;
+    int nt, layer, n_layers, units_per_layer;
+    __device__ __forceinline__ void set_layer_range() {
+        g = Gl * blockIdx.x / gridDim.x;
+        g1 = Gl * (blockIdx.x + 1) / gridDim.x;
 #if RTK_SCORE_EVEN_RANGES
         // consecutive tiles alternate between the two softmax group pairs: with an even number of tiles per unit every
         // (partial) unit of an even-aligned range gives both pairs the same amount of work before they meet at the merge
-        if ((nt_ & 1) == 0) {
-            g = 2 * ((G / 2) * blockIdx.x / gridDim.x);
-            g1 = 2 * ((G / 2) * (blockIdx.x + 1) / gridDim.x);
+        if ((nt & 1) == 0) {
+            g = 2 * ((Gl / 2) * blockIdx.x / gridDim.x);
+            g1 = 2 * ((Gl / 2) * (blockIdx.x + 1) / gridDim.x);
         }
 #endif
     }
+    // H: heads of all layers, Hl: heads per layer
+    __device__ __forceinline__ TileRange(int H, int Hl, int nt_) : nt(nt_), layer(0) {
+        n_layers = H / Hl;
+        units_per_layer = Hl * nt_;
+        Gl = (long long)units_per_layer * nt_;
+        set_layer_range();
+    }
+    // u: unit index over all layers (= head-of-all-layers * nt + stationary tile)
     __device__ __forceinline__ bool next(int& u, int& tb0, int& tb1) {
-        if (g >= g1) return false;
-        u = (int)(g / nt);
-        tb0 = (int)(g - (long long)u * nt);
+        while (g >= g1) {
+            if (++layer >= n_layers) return false;
+            set_layer_range();
+        }
+        const int ul = (int)(g / nt);
+        tb0 = (int)(g - (long long)ul * nt);
         const long long left = g1 - g;
         tb1 = (left < nt - tb0) ? tb0 + (int)left : nt;
         g += tb1 - tb0;
+        u = layer * units_per_layer + ul;
         return true;
     }
 };
@@ -422,9 +443,9 @@ constexpr int kScoreThreads2 = (2 + kSoftmaxWarps) * 32;
 constexpr int kChunksPerTile = 128 / RTK_SCORE_GCOLS;
 constexpr int kTileArrivals = RTK_SCORE_GROUPS ? 4 * kChunksPerTile : 8;       // softmax-warp arrivals that free one accumulator buffer
 
-template <int PASS>
+template <int PASS, int NL>
 __global__ void __launch_bounds__(kScoreThreads2, 1)
-pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_constant__ CUtensorMap k_map, ScoreParams prm) {
+pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) {
     if (RTK_PDL_EARLY_SCORE) pdl_trigger();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // dynamic smem base is only guaranteed 16-byte aligned: round up to 1024 for the swizzle atoms
@@ -460,11 +481,11 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
     const int nt = prm.nt;
     const size_t hl = (size_t)prm.H * nt * kTile;            // elements of one [H][Lpad] plane
     // the stationary operand is Q in pass 1 and K in pass 2
-    const CUtensorMap* a_map = (PASS == 1) ? &q_map : &k_map;
-    const CUtensorMap* b_map = (PASS == 1) ? &k_map : &q_map;
+    const CUtensorMap* a_maps = (PASS == 1) ? maps.q : maps.k;
+    const CUtensorMap* b_maps = (PASS == 1) ? maps.k : maps.q;
     const int a_l1 = (PASS == 1) ? prm.q_dim1_is_l : prm.k_dim1_is_l;
     const int b_l1 = (PASS == 1) ? prm.k_dim1_is_l : prm.q_dim1_is_l;
-    TileRange range(prm.H, nt);
+    TileRange range(prm.H, prm.Hl, nt);
     int u, tb0, tb1;
 
     if (warp == 0) {
@@ -472,7 +493,11 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
         if (lane == 0) {
             uint32_t cnt = 0, ucnt = 0;
             while (range.next(u, tb0, tb1)) {
-                const int h = u / nt, ta = u - h * nt;
+                const int hh = u / nt, ta = u - hh * nt;             // hh: head index over all layers of the launch
+                const int layer = (NL == 1) ? 0 : hh / prm.Hl;
+                const int h = hh - layer * prm.Hl;
+                const CUtensorMap* a_map = a_maps + layer;
+                const CUtensorMap* b_map = b_maps + layer;
                 const int a_head = (PASS == 1) ? h : h / prm.G;
                 const int b_head = (PASS == 1) ? h / prm.G : h;
                 // stationary tile of this unit into slot ucnt % kASlots: with two slots it is on its way while the
@@ -502,7 +527,7 @@ pivot_score_kernel(const __grid_constant__ CUtensorMap q_map, const __grid_const
                         const int sl = cnt % kStatSlots;
                         mbar_arrive_expect_tx(st_full(sl), kTile * 4u);
                         bulk_g2s(base + ScoreSmem::stats + sl * kTile * 4u,
-                                 prm.stats + (size_t)h * nt * kTile + (size_t)tb * kTile, kTile * 4u, st_full(sl));
+                                 prm.stats + (size_t)hh * nt * kTile + (size_t)tb * kTile, kTile * 4u, st_full(sl));
                     }
                 }
             }
@@ -770,9 +795,15 @@ __global__ void pivot_stats_merge_kernel(const float2* __restrict__ ml_part, int
     stats[o] = (q < L) ? fmaf(mn, kLog2e, lg2f(lt)) : INFINITY;
 }
 
-// a = bf16(colsum);  head_scores[g] = bf16((sum over the G heads of group g, ATen 4-accumulator order) * f32(1/G))
+// a = bf16(colsum);  head_scores[g] = bf16((sum over the G heads of group g, ATen 4-accumulator order) * f32(1/G)).
+// blockIdx.y runs over the KV heads of all layers of the launch; every layer has its own [KVH, L] output.
+struct HeadScoreOut {
+    __nv_bfloat16* p[kMaxBatchLayers];
+    int KVH;                          // KV heads per layer
+};
+
 __global__ void pivot_head_reduce_kernel(const float* __restrict__ colsum_part, int H, int G, int L, int Lpad,
-                                         __nv_bfloat16* __restrict__ head_scores) {
+                                         const __grid_constant__ HeadScoreOut out) {
     pdl_enter();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = blockIdx.y;
@@ -784,7 +815,8 @@ __global__ void pivot_head_reduce_kernel(const float* __restrict__ colsum_part, 
         v[j & 3] += round_bf16(colsum_part[o] + colsum_part[hl + o]);
     }
     const float s = ((v[0] + v[1]) + v[2]) + v[3];
-    head_scores[(size_t)g * L + k] = __float2bfloat16_rn(s * (1.0f / (float)G));
+    const int layer = g / out.KVH;
+    out.p[layer][(size_t)(g - layer * out.KVH) * L + k] = __float2bfloat16_rn(s * (1.0f / (float)G));
 }
 
 // ---------------------------------------------------------------------------------------------- host side
@@ -833,50 +865,81 @@ extern "C" size_t rtk_pivot_score_workspace_bytes(int64_t H, int64_t L) {
     return 7 * (size_t)H * lpad * sizeof(float);       // ml_part (2 x float2) + stats + colsum_part (2)
 }
 
+namespace rtk {
+
+template <int NL>
+static int score_launch(const ScoreBatch& b, ScoreParams prm, cudaStream_t st) {
+    ScoreMaps<NL> maps;
+    for (int l = 0; l < b.n; ++l) {
+        int ql = 0, kl = 0;
+        int rc = make_map(&maps.q[l], b.q[l], b.H, b.L, b.D, b.q_stride_h[l], b.q_stride_l[l], &ql);
+        if (rc) return rc;
+        rc = make_map(&maps.k[l], b.k[l], b.KVH, b.L, b.D, b.k_stride_h[l], b.k_stride_l[l], &kl);
+        if (rc) return rc;
+        if (l == 0) { prm.q_dim1_is_l = ql; prm.k_dim1_is_l = kl; }
+        else if (ql != prm.q_dim1_is_l || kl != prm.k_dim1_is_l) return RTK_E_UNSUPPORTED;   // layers must share a layout
+    }
+    for (int l = b.n; l < NL; ++l) { maps.q[l] = maps.q[0]; maps.k[l] = maps.k[0]; }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int units = prm.Hl * prm.nt;                 // per layer: the grid (and so every cut point) is that of one layer
+    const int grid = units < sms ? units : sms;
+    const size_t smem = ScoreSmem::total + 1024;
+    cudaError_t e = cudaFuncSetAttribute(pivot_score_kernel<1, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(pivot_score_kernel<2, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    HeadScoreOut out;
+    out.KVH = (int)b.KVH;
+    for (int l = 0; l < kMaxBatchLayers; ++l) out.p[l] = reinterpret_cast<__nv_bfloat16*>(b.head_scores[l < b.n ? l : 0]);
+    RTK_LAUNCH_PDL((pivot_score_kernel<1, NL>), grid, kScoreThreads2, smem, st, maps, prm);
+    dim3 g1((unsigned)((prm.nt * kTile + 255) / 256), (unsigned)prm.H);
+    RTK_LAUNCH_PDL(pivot_stats_merge_kernel, g1, 256, 0, st, prm.ml_part, prm.H, prm.L, prm.nt * kTile, prm.stats);
+    RTK_LAUNCH_PDL((pivot_score_kernel<2, NL>), grid, kScoreThreads2, smem, st, maps, prm);
+    dim3 g2((unsigned)((prm.L + 255) / 256), (unsigned)(b.KVH * b.n));
+    RTK_LAUNCH_PDL(pivot_head_reduce_kernel, g2, 256, 0, st, prm.colsum_part, prm.H, prm.G, prm.L, prm.nt * kTile, out);
+    return 0;
+}
+
+// scoring of b.n layers of one chunk (same H, KVH, L, D) by one chain of four launches
+int pivot_score_batch(const ScoreBatch& b, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+    if (b.n < 1 || b.n > kMaxBatchLayers || !workspace || b.H < 1 || b.KVH < 1 || b.L < 1) return RTK_E_BADARG;
+    if ((b.D != 64 && b.D != 128) || b.H % b.KVH != 0 || b.L > 16384) return RTK_E_UNSUPPORTED;
+    if (((uintptr_t)workspace & 15u) != 0) return RTK_E_ALIGN;
+    for (int l = 0; l < b.n; ++l) {
+        if (!b.q[l] || !b.k[l] || !b.head_scores[l]) return RTK_E_BADARG;
+        if ((((uintptr_t)b.q[l] | (uintptr_t)b.k[l]) & 15u) != 0) return RTK_E_ALIGN;
+        if ((b.q_stride_h[l] | b.q_stride_l[l] | b.k_stride_h[l] | b.k_stride_l[l]) % 8 != 0) return RTK_E_ALIGN;
+    }
+    if (workspace_bytes < rtk_pivot_score_workspace_bytes(b.H * b.n, b.L)) return RTK_E_WORKSPACE;
+
+    ScoreParams prm;
+    prm.H = (int)(b.H * b.n);
+    prm.Hl = (int)b.H;
+    prm.G = (int)(b.H / b.KVH);
+    prm.L = (int)b.L;
+    prm.nt = (int)((b.L + kTile - 1) / kTile);
+    prm.n_atoms = (int)(b.D / 64);
+    prm.q_dim1_is_l = prm.k_dim1_is_l = 0;
+    const float sq = (float)sqrt((double)b.D);
+    prm.inv_sqrt_d = 1.0f / sq;
+    const size_t plane = (size_t)prm.H * prm.nt * kTile;
+    prm.ml_part = reinterpret_cast<float2*>(workspace);
+    prm.stats = reinterpret_cast<float*>(workspace) + 4 * plane;
+    prm.colsum_part = prm.stats + plane;
+    return b.n == 1 ? score_launch<1>(b, prm, st) : score_launch<kMaxBatchLayers>(b, prm, st);
+}
+
+}  // namespace rtk
+
 extern "C" int rtk_pivot_score(const void* q, int64_t H, int64_t q_stride_h, int64_t q_stride_l, const void* k, int64_t KVH,
                                int64_t k_stride_h, int64_t k_stride_l, int64_t L, int64_t D, void* head_scores,
                                void* workspace, size_t workspace_bytes, void* stream) {
     if (!q || !k || !head_scores || !workspace || H < 1 || KVH < 1 || L < 1) return RTK_E_BADARG;
-    if ((D != 64 && D != 128) || H % KVH != 0 || L > 16384) return RTK_E_UNSUPPORTED;
-    if ((((uintptr_t)q | (uintptr_t)k | (uintptr_t)workspace) & 15u) != 0) return RTK_E_ALIGN;
-    if ((q_stride_h | q_stride_l | k_stride_h | k_stride_l) % 8 != 0) return RTK_E_ALIGN;
-    if (workspace_bytes < rtk_pivot_score_workspace_bytes(H, L)) return RTK_E_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
-
-    ScoreParams prm;
-    prm.H = (int)H;
-    prm.G = (int)(H / KVH);
-    prm.L = (int)L;
-    prm.nt = (int)((L + kTile - 1) / kTile);
-    prm.n_atoms = (int)(D / 64);
-    const float sq = (float)sqrt((double)D);
-    prm.inv_sqrt_d = 1.0f / sq;
-    const size_t plane = (size_t)H * prm.nt * kTile;
-    prm.ml_part = reinterpret_cast<float2*>(workspace);
-    prm.stats = reinterpret_cast<float*>(workspace) + 4 * plane;
-    prm.colsum_part = prm.stats + plane;
-
-    CUtensorMap qm, km;
-    int rc = make_map(&qm, q, H, L, D, q_stride_h, q_stride_l, &prm.q_dim1_is_l);
-    if (rc) return rc;
-    rc = make_map(&km, k, KVH, L, D, k_stride_h, k_stride_l, &prm.k_dim1_is_l);
-    if (rc) return rc;
-
-    int dev = 0, sms = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int units = prm.H * prm.nt;
-    const int grid = units < sms ? units : sms;
-    const size_t smem = ScoreSmem::total + 1024;
-    cudaError_t e = cudaFuncSetAttribute(pivot_score_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(pivot_score_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    RTK_LAUNCH_PDL(pivot_score_kernel<1>, grid, kScoreThreads2, smem, st, qm, km, prm);
-    dim3 g1((unsigned)((prm.nt * kTile + 255) / 256), (unsigned)H);
-    RTK_LAUNCH_PDL(pivot_stats_merge_kernel, g1, 256, 0, st, prm.ml_part, (int)H, (int)L, prm.nt * kTile, prm.stats);
-    RTK_LAUNCH_PDL(pivot_score_kernel<2>, grid, kScoreThreads2, smem, st, qm, km, prm);
-    dim3 g2((unsigned)((L + 255) / 256), (unsigned)KVH);
-    RTK_LAUNCH_PDL(pivot_head_reduce_kernel, g2, 256, 0, st, prm.colsum_part, (int)H, prm.G, (int)L, prm.nt * kTile, reinterpret_cast<__nv_bfloat16*>(head_scores));
-    return 0;
+    ScoreBatch b = {};
+    b.n = 1; b.H = H; b.KVH = KVH; b.L = L; b.D = D;
+    b.q[0] = q; b.k[0] = k; b.head_scores[0] = head_scores;
+    b.q_stride_h[0] = q_stride_h; b.q_stride_l[0] = q_stride_l; b.k_stride_h[0] = k_stride_h; b.k_stride_l[0] = k_stride_l;
+    return pivot_score_batch(b, workspace, workspace_bytes, (cudaStream_t)stream);
 }

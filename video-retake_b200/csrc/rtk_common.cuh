@@ -30,6 +30,19 @@ struct DisAux {
 };
 int dpselect_sim_nrm(const void* x, int64_t T, int64_t N, int64_t C, DisAux aux, cudaStream_t st);
 
+// Layers of one chunk scored by one chain of launches (rtk_pivot_update_batch -> pivot_score.cu).  Per-layer tables travel
+// as kernel parameters (CUDA >= 12.1 accepts up to 32 KB of them), so a batch is capped at kMaxBatchLayers layers.
+constexpr int kMaxBatchLayers = 32;
+struct ScoreBatch {
+    int n;                                           // layers
+    int64_t H, KVH, L, D;                            // shared by all layers
+    const void* q[kMaxBatchLayers];                  // bf16 [H, L, D] views
+    const void* k[kMaxBatchLayers];                  // bf16 [KVH, L, D] views
+    void* head_scores[kMaxBatchLayers];              // bf16 [KVH, L] each
+    int64_t q_stride_h[kMaxBatchLayers], q_stride_l[kMaxBatchLayers], k_stride_h[kMaxBatchLayers], k_stride_l[kMaxBatchLayers];
+};
+int pivot_score_batch(const ScoreBatch& b, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 // ------------------------------------------------------------------------ programmatic dependent launch (PDL)
 // The operators are chains of small dependent kernels on one stream.  Launched with the programmatic-stream-
 // serialization attribute a kernel may become resident while its predecessor is still running; every kernel

@@ -14,6 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RTK_B200_LIB", os.path.join(os.path.dirname(_HERE), "lib", "librtk_b200.so"))
 
 _lib = None
+ABI_VERSION = 2          # RTK_ABI_VERSION of include/rtk_b200.h
 
 
 class RtkError(RuntimeError):
@@ -49,13 +50,15 @@ def lib() -> C.CDLL:
         "rtk_pivot_rope_tables": ([p, i32, i64, i64, p, p, f32, p, p, p], C.c_int),
         "rtk_pivot_update_workspace_bytes": ([i64, i64, i64, i64], sz),
         "rtk_pivot_update": ([p, p], C.c_int),
+        "rtk_pivot_update_batch_workspace_bytes": ([i64, i64, i64, i64, i64], sz),
+        "rtk_pivot_update_batch": ([p, i64, p, sz, p], C.c_int),
         "rtk_kv_block_copy": ([i32, p, p, p, p, p, p, p, p, i64, p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)            # AttributeError here == header and library disagree
         fn.argtypes, fn.restype = args, res
-    if L.rtk_version() != 1:
-        raise RtkError(f"ABI mismatch: library reports version {L.rtk_version()}, binding expects 1")
+    if L.rtk_version() != ABI_VERSION:
+        raise RtkError(f"ABI mismatch: library reports version {L.rtk_version()}, binding expects {ABI_VERSION}")
     _lib = L
     return L
 
@@ -63,7 +66,7 @@ def lib() -> C.CDLL:
 EXPORTS = ("rtk_version", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
            "rtk_dpselect_gather", "rtk_gather_rows", "rtk_mallm_workspace_bytes", "rtk_mallm_compress", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
            "rtk_pivot_select", "rtk_pivot_compact", "rtk_pivot_rope_tables", "rtk_pivot_update_workspace_bytes",
-           "rtk_pivot_update", "rtk_kv_block_copy")
+           "rtk_pivot_update", "rtk_pivot_update_batch_workspace_bytes", "rtk_pivot_update_batch", "rtk_kv_block_copy")
 
 
 def check(rc: int, what: str) -> None:

@@ -209,7 +209,8 @@ class _UpdateArgs(C.Structure):
                 ("k_out", C.c_void_p), ("v_out", C.c_void_p), ("out_stride_h", C.c_int64),
                 ("pos_out", C.c_void_p), ("keep_idx", C.c_void_p), ("head_scores", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("ev_score_begin", C.c_void_p), ("ev_score_end", C.c_void_p)]
+                ("ev_score_begin", C.c_void_p), ("ev_score_end", C.c_void_p),
+                ("pos_out_stride", C.c_int64)]
 
 
 _STATIC_INV_FREQ_ROPE = ("default", "yarn", "linear", "llama3")
@@ -279,6 +280,7 @@ class PivotKVLayer(DynamicLayer):
         self._kbuf = self._vbuf = None
         self._len = 0
         self._pending = None            # (kept_k, kept_v, start) waiting to be written at [start, start + keep)
+        self._deferred_owner = None     # PivotKVCache that still owes this layer a deferred (batched) compression
 
     # -- HF reads these attributes; a read settles the deferred write first
     @property
@@ -335,6 +337,9 @@ class PivotKVLayer(DynamicLayer):
         return [(kk, self._kbuf[:, :, start:start + n]), (vv, self._vbuf[:, :, start:start + n])]
 
     def flush(self):
+        owner = self._deferred_owner
+        if owner is not None:
+            owner.flush_deferred()      # the batched compression of the last chunk writes this layer's kept rows
         jobs = self.pending_jobs()
         if jobs:
             _block_copy(jobs)
@@ -382,6 +387,16 @@ class PivotKVLayer(DynamicLayer):
         self._keys_view = self._kbuf[:, :, :self._len]
         self._values_view = self._vbuf[:, :, :self._len]
 
+    def shrink_tail(self, n_tail, keep, owner):
+        """deferred compression: the last ``n_tail`` rows will become ``keep`` rows written IN PLACE by ``owner``'s batched
+        compression.  Returns the (keys, values) destination views ``[1, KVH, keep, D]`` inside the buffers."""
+        start = self._len - n_tail
+        self._len = start + keep
+        self._keys_view = self._kbuf[:, :, :self._len]
+        self._values_view = self._vbuf[:, :, :self._len]
+        self._deferred_owner = owner
+        return self._kbuf[:, :, start:start + keep], self._vbuf[:, :, start:start + keep]
+
 
 class _LayerListView:
     """``cache.key_cache[i]`` / ``cache.value_cache[i]`` of transformers 4.48 on top of ``layers[i]``."""
@@ -427,9 +442,37 @@ class PivotKVCache(DynamicCache):
         self._pos_len: List[int] = []
         self._dirty: List[PivotKVLayer] = []
         self.score_events = None            # optional (cudaEvent_t, cudaEvent_t) ints recorded around the next scoring
+        # Deferred compression: ``update`` only appends the chunk and remembers its tensors; the
+        # compression of ALL layers of the chunk runs as one batched call (``rtk_pivot_update_batch``, seven launches
+        # per chunk instead of eight per layer) when the chunk's forward is over - ``after_forward()``, the hook the
+        # reference's chunk loop already calls (``qwen2_vl.py:715-716``) - or at the next cache operation that needs
+        # the result.  A chunk's kept rows are first read by the NEXT chunk, so the cache contents every reader sees
+        # are the same as with compression inside ``update``.  Knob: ``kvcache_compression_kwargs.deferred_compression``
+        # (default: the RTK_DEFERRED environment variable, off).
+        self.deferred_compression = bool(kv_compression_kwargs.get("deferred_compression",
+                                                                   os.environ.get("RTK_DEFERRED", "0") == "1"))
+        self._deferred: List[Dict[str, Any]] = []
         # exposed for tests / the multi-GPU path: the last chunk's per-KV-head scores and kept indices
-        self.last_head_scores: Optional[torch.Tensor] = None
-        self.last_keep_indices: Optional[torch.Tensor] = None
+        self._last_head_scores: Optional[torch.Tensor] = None
+        self._last_keep_indices: Optional[torch.Tensor] = None
+
+    @property
+    def last_head_scores(self):
+        self.flush_deferred()
+        return self._last_head_scores
+
+    @last_head_scores.setter
+    def last_head_scores(self, t):
+        self._last_head_scores = t
+
+    @property
+    def last_keep_indices(self):
+        self.flush_deferred()
+        return self._last_keep_indices
+
+    @last_keep_indices.setter
+    def last_keep_indices(self, t):
+        self._last_keep_indices = t
 
     # transformers 4.48 attribute names
     @property
@@ -447,10 +490,37 @@ class PivotKVCache(DynamicCache):
         self.flush()
 
     def flush(self):
-        """settle every deferred tail overwrite (cheap no-op when nothing is pending)"""
+        """settle every deferred compression / tail overwrite (cheap no-op when nothing is pending)"""
+        self.flush_deferred()
         dirty, self._dirty = self._dirty, []
         for layer in dirty:
             layer.flush()
+
+    def flush_deferred(self):
+        """run the batched compression of every layer that ``update`` left pending (one C-ABI call per group of layers
+        with the same shape - in practice one per chunk)"""
+        pend, self._deferred = self._deferred, []
+        if not pend:
+            return
+        lib = N.lib()
+        groups: Dict[Any, List[Dict[str, Any]]] = {}
+        for e in pend:
+            groups.setdefault(e["sig"], []).append(e)
+        for sig, entries in groups.items():
+            H, KVH, L, D = sig[:4]
+            dev = entries[0]["device"]
+            n = len(entries)
+            arr = (_UpdateArgs * n)(*[e["args"] for e in entries])
+            ws = _workspace(dev, int(lib.rtk_pivot_update_batch_workspace_bytes(H, KVH, L, D, n)) + 256)
+            ws_ptr = (ws.data_ptr() + 255) & ~255
+            if self.score_events is not None:
+                arr[0].ev_score_begin, arr[0].ev_score_end = self.score_events
+                self.score_events = None
+            with torch.cuda.device(dev):
+                N.check(lib.rtk_pivot_update_batch(arr, n, ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()), N.stream_ptr(dev)),
+                        "rtk_pivot_update_batch")
+        for e in pend:
+            e["layer"]._deferred_owner = None
 
     def update_num_evicted_tokens(self, num_tokens: int, layer_idx: int) -> int:
         while len(self.num_evicted_tokens) <= layer_idx:
@@ -458,28 +528,35 @@ class PivotKVCache(DynamicCache):
         self.num_evicted_tokens[layer_idx] += num_tokens
         return self.num_evicted_tokens[layer_idx]
 
-    def update_position_ids(self, position_ids: torch.Tensor, layer_idx: int) -> torch.Tensor:
-        """append along the last dim into a grown buffer; ``position_cache[layer_idx]`` is the valid view"""
+    def _position_slots(self, like: torch.Tensor, n: int, layer_idx: int) -> torch.Tensor:
+        """``n`` more entries along the last dim of layer ``layer_idx``'s grown position buffer (leading dims, dtype and
+        device of ``like``); returns the view to fill, ``position_cache[layer_idx]`` becomes the longer valid view"""
         while len(self.position_cache) <= layer_idx:
             self.position_cache.append([])
             self._pos_buf.append(None)
             self._pos_len.append(0)
-        n = position_ids.shape[-1]
         buf, cur = self._pos_buf[layer_idx], self._pos_len[layer_idx]
-        if buf is None or cur + n > buf.shape[-1] or buf.shape[:-1] != position_ids.shape[:-1]:
+        if buf is None or cur + n > buf.shape[-1] or buf.shape[:-1] != like.shape[:-1]:
+            self.flush_deferred()                          # pending batched writes target the old buffer
             cap = max(cur + n, int((0 if buf is None else buf.shape[-1]) * 1.5), 8192)
-            nb = torch.empty(position_ids.shape[:-1] + (cap,), dtype=position_ids.dtype, device=position_ids.device)
+            nb = torch.empty(like.shape[:-1] + (cap,), dtype=like.dtype, device=like.device)
             if cur:
                 nb[..., :cur].copy_(buf[..., :cur])
             buf = self._pos_buf[layer_idx] = nb
-        buf[..., cur:cur + n].copy_(position_ids)
         self._pos_len[layer_idx] = cur + n
         self.position_cache[layer_idx] = buf[..., :cur + n]
+        return buf[..., cur:cur + n]
+
+    def update_position_ids(self, position_ids: torch.Tensor, layer_idx: int) -> torch.Tensor:
+        """append along the last dim into a grown buffer; ``position_cache[layer_idx]`` is the valid view"""
+        self._position_slots(position_ids, position_ids.shape[-1], layer_idx).copy_(position_ids)
         return self.position_cache[layer_idx]
 
     def get_prev_temporal_idx(self, layer_idx: int):
         if len(self.position_cache) <= layer_idx or len(self.position_cache[layer_idx]) == 0:
             return -1
+        if layer_idx < len(self.layers) and self.layers[layer_idx]._deferred_owner is not None:
+            self.flush_deferred()                       # (the attention forward asks per layer: only this layer's debt matters)
         cache_layer = self.position_cache[layer_idx]
         return cache_layer[0, 0, -1] if cache_layer.ndim == 3 else cache_layer[0, -1]
 
@@ -489,20 +566,20 @@ class PivotKVCache(DynamicCache):
         return self.layers[layer_idx].get_seq_length()
 
     # ------------------------------------------------------------------------------------------------ update
-    def _compress_chunk(self, query_states, key_states, value_states, position_ids, rotary_emb_fn, mrope_section,
-                        keep_len):
-        """one ``rtk_pivot_update`` call -> (kept K [1,KVH,keep,D], kept V, kept positions or None)"""
+    def _update_args(self, query_states, key_states, value_states, position_ids, rotary_emb_fn, mrope_section, keep_len,
+                     k_out=None, v_out=None, pos_out=None):
+        """fill one ``rtk_pivot_update_args``; returns (args, outputs, tensors that must outlive the launches, fast)
+        ``k_out`` / ``v_out`` ``[1, KVH, keep, D]`` (rows D apart, any head stride) and ``pos_out`` ``[..., keep]`` default to
+        fresh tensors; ``fast`` is False when the rotary module is opaque (tables come from calling it)"""
         q, H, L, D, qsh, qsl = _hld(query_states, "query_states")
         k, KVH, Lk, Dk, ksh, ksl = _hld(key_states, "key_states")
         v, _, _, _, vsh, vsl = _hld(value_states, "value_states")
         if Lk != L or Dk != D:
             raise ValueError("PivotKV scores the chunk's own keys: key and query lengths must match")
         dev = q.device
-        lib = N.lib()
-        ws = _workspace(dev, int(lib.rtk_pivot_update_workspace_bytes(H, KVH, L, D)) + 256)
-        ws_ptr = (ws.data_ptr() + 255) & ~255
-        k_out = torch.empty((1, KVH, keep_len, D), dtype=torch.bfloat16, device=dev)
-        v_out = torch.empty_like(k_out)
+        if k_out is None:
+            k_out = torch.empty((1, KVH, keep_len, D), dtype=torch.bfloat16, device=dev)
+            v_out = torch.empty_like(k_out)
         head_scores = torch.empty((KVH, L), dtype=torch.bfloat16, device=dev)
         keep_idx = torch.empty((keep_len,), dtype=torch.int32, device=dev)
         a = _UpdateArgs()
@@ -520,43 +597,89 @@ class PivotKVCache(DynamicCache):
             a.keymask = keymask.data_ptr()
         reforge = bool(self.pos_embed_reforge)
         a.reforge = int(reforge)
-        pos_out = pos_flat = cos = sin = inv = None
+        pos_flat = cos = sin = inv = None
         if position_ids is not None:
             N.require_cuda(position_ids, "position_ids", torch.int64)
             pos_flat = position_ids.reshape(-1, L).contiguous()
             a.n_pos, a.pos = pos_flat.shape[0], pos_flat.data_ptr()
-            pos_out = torch.empty(position_ids.shape[:-1] + (keep_len,), dtype=torch.int64, device=dev)
+            if pos_out is None:
+                pos_out = torch.empty(position_ids.shape[:-1] + (keep_len,), dtype=torch.int64, device=dev)
             a.pos_out = pos_out.data_ptr()
+            a.pos_out_stride = pos_out.stride(0) if pos_flat.shape[0] > 1 else keep_len
             if mrope_section and pos_flat.shape[0] == 3:
                 a.mrope_section = (C.c_int32 * 3)(*[int(s) for s in mrope_section])
-        fast = None
+        fast = True
         if reforge:
             scaling = float(rotary_emb_fn.attention_scaling)
             a.attention_scaling, a.inv_scale2 = scaling, _inv_scale2(scaling)
-            fast = _rotary_inv_freq(rotary_emb_fn)
-            if fast is not None:
-                inv = fast[0].to(device=dev, dtype=torch.float32).contiguous()
+            static = _rotary_inv_freq(rotary_emb_fn)
+            if static is not None:
+                inv = self._inv_freq_on(static[0], dev)
                 a.inv_freq = inv.data_ptr()
             else:
+                fast = False
                 cos, sin = rotary_emb_fn(value_states, position_ids)
                 cos, sin = cos.contiguous(), sin.contiguous()
                 if cos.dtype != torch.bfloat16 or cos.numel() != pos_flat.shape[0] * L * D:
                     raise ValueError("rotary_emb must return bf16 [n_pos, 1, L, D] tables")
                 a.cos, a.sin = cos.data_ptr(), sin.data_ptr()
-        a.k_out, a.v_out, a.out_stride_h = k_out.data_ptr(), v_out.data_ptr(), keep_len * D
+        a.k_out, a.v_out, a.out_stride_h = k_out.data_ptr(), v_out.data_ptr(), k_out.stride(1)
         a.keep_idx, a.head_scores = keep_idx.data_ptr(), head_scores.data_ptr()
+        sig = (H, KVH, L, D, keep_len, reforge, int(a.n_pos), a.inv_freq, float(a.attention_scaling), tuple(a.mrope_section),
+               dev.index)
+        outs = {"k_out": k_out, "v_out": v_out, "pos_out": pos_out, "head_scores": head_scores, "keep_idx": keep_idx}
+        keepalive = (q, k, v, keymask, pos_flat, cos, sin, inv)
+        return a, outs, keepalive, fast, sig
+
+    def _inv_freq_on(self, inv_freq: torch.Tensor, dev) -> torch.Tensor:
+        """fp32 copy of the rotary module's inv_freq on ``dev`` (the module's own tensor when it already is one)"""
+        if inv_freq.device == dev and inv_freq.dtype == torch.float32 and inv_freq.is_contiguous():
+            return inv_freq
+        key = (id(inv_freq), dev)
+        hit = getattr(self, "_inv_cache", None)
+        if hit is None or hit[0] != key:
+            self._inv_cache = (key, inv_freq.to(device=dev, dtype=torch.float32).contiguous(), inv_freq)
+        return self._inv_cache[1]
+
+    def _compress_chunk(self, query_states, key_states, value_states, position_ids, rotary_emb_fn, mrope_section,
+                        keep_len):
+        """one ``rtk_pivot_update`` call -> (kept K [1,KVH,keep,D], kept V, kept positions or None)"""
+        a, outs, keepalive, fast, _ = self._update_args(query_states, key_states, value_states, position_ids, rotary_emb_fn,
+                                                        mrope_section, keep_len)
+        dev = query_states.device
+        lib = N.lib()
+        ws = _workspace(dev, int(lib.rtk_pivot_update_workspace_bytes(a.H, a.KVH, a.L, a.D)) + 256)
+        ws_ptr = (ws.data_ptr() + 255) & ~255
         a.workspace, a.workspace_bytes = ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr())
         if self.score_events is not None:
             a.ev_score_begin, a.ev_score_end = self.score_events
             self.score_events = None
         with torch.cuda.device(dev):
             N.check(lib.rtk_pivot_update(C.byref(a), N.stream_ptr(dev)), "rtk_pivot_update")
-        if reforge and fast is None:
+        k_out, v_out, pos_out = outs["k_out"], outs["v_out"], outs["pos_out"]
+        if self.pos_embed_reforge and not fast:
             # opaque rotary callable: ask it for the tables of the re-indexed positions, then re-rotate in place
             cos2, sin2 = rotary_emb_fn(v_out, pos_out)
             pivot_rope(k_out, cos2, sin2, mrope_section, 1.0, forward=True, out=k_out)
-        self.last_head_scores, self.last_keep_indices = head_scores, keep_idx
+        self.last_head_scores, self.last_keep_indices = outs["head_scores"], outs["keep_idx"]
         return k_out, v_out, pos_out
+
+    def _defer_chunk(self, layer, layer_idx, query_states, key_states, value_states, position_ids, rotary_emb_fn,
+                     mrope_section, keep_len) -> bool:
+        """queue this layer's compression for the batched call; False when it has to run now (opaque rotary module)"""
+        if self.pos_embed_reforge and _rotary_inv_freq(rotary_emb_fn) is None:
+            return False
+        q_len = query_states.shape[2]
+        pos_out = None
+        if self.pos_embed_reforge:
+            pos_out = self._position_slots(position_ids, keep_len, layer_idx)      # kept positions land in the position cache
+        k_dst, v_dst = layer.shrink_tail(q_len, keep_len, self)                    # kept rows land in the cache itself
+        a, outs, keepalive, _, sig = self._update_args(query_states, key_states, value_states, position_ids, rotary_emb_fn,
+                                                       mrope_section, keep_len, k_dst, v_dst, pos_out)
+        self._deferred.append({"args": a, "outs": outs, "keepalive": keepalive, "sig": sig, "layer": layer,
+                               "device": query_states.device})
+        self._last_head_scores, self._last_keep_indices = outs["head_scores"], outs["keep_idx"]
+        return True
 
     def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int,
                cache_kwargs: Optional[Dict[str, Any]] = None) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -575,6 +698,8 @@ class PivotKVCache(DynamicCache):
         while len(self.layers) <= layer_idx:
             self.layers.append(PivotKVLayer())
         layer = self.layers[layer_idx]
+        if layer._deferred_owner is not None:
+            self.flush_deferred()                       # no after_forward() since this layer's last chunk: settle it now
         dirty, self._dirty = self._dirty, []
         jobs = [j for l in dirty for j in l.pending_jobs()]
         more, key_states_output, value_states_output = layer.append_jobs(key_states, value_states)
@@ -592,6 +717,11 @@ class PivotKVCache(DynamicCache):
 
             # 2) score the chunk's own keys with the chunk's queries, keep the top ratio * q_len
             keep_len = max(1, int(self.compression_ratio * q_len))
+            if self.deferred_compression and self._defer_chunk(layer, layer_idx, query_states, key_states, value_states,
+                                                               position_ids, rotary_emb_fn, mrope_section, keep_len):
+                # 2') ... later: all layers of the chunk in one batched call, kept rows written in place (flush_deferred)
+                self.update_num_evicted_tokens(k_len - keep_len, layer_idx)
+                return key_states_output, value_states_output
             kept_k, kept_v, kept_pos = self._compress_chunk(query_states, key_states, value_states, position_ids,
                                                             rotary_emb_fn, mrope_section, keep_len)
             if self.pos_embed_reforge:
