@@ -537,7 +537,8 @@ class PivotKVCache(DynamicCache):
             self._pos_len.append(0)
         buf, cur = self._pos_buf[layer_idx], self._pos_len[layer_idx]
         if buf is None or cur + n > buf.shape[-1] or buf.shape[:-1] != like.shape[:-1]:
-            self.flush_deferred()                          # pending batched writes target the old buffer
+            if layer_idx < len(self.layers) and self.layers[layer_idx]._deferred_owner is not None:
+                self.flush_deferred()                      # this layer's pending batched write targets the old buffer
             cap = max(cur + n, int((0 if buf is None else buf.shape[-1]) * 1.5), 8192)
             nb = torch.empty(like.shape[:-1] + (cap,), dtype=like.dtype, device=like.device)
             if cur:
