@@ -86,6 +86,19 @@ __device__ __forceinline__ void unrope_qk_body(const __nv_bfloat16* __restrict__
     const int vec_per_row = half >> 3;
     const int ntask = (p.heads + p.heads2) * vec_per_row;
     for (int l = blockIdx.x; l < p.L; l += gridDim.x) {
+        // the first task's rows are requested before the table is built, so that the trigonometry hides their latency
+        // (at the 7B shape - 32 heads x 8 vectors - a thread has exactly one task)
+        uint4 lo4 = make_uint4(0, 0, 0, 0), hi4 = lo4;
+        {
+            const int task = threadIdx.x;
+            if (task < ntask) {
+                const int v = task % vec_per_row, h = task / vec_per_row;
+                const bool second = h >= p.heads;
+                const __nv_bfloat16* src = second ? p.x2 + (h - p.heads) * p.stride_h2 + l * p.stride_l2 : x + h * p.stride_h + l * p.stride_l;
+                lo4 = *reinterpret_cast<const uint4*>(src + v * 8);
+                hi4 = *reinterpret_cast<const uint4*>(src + v * 8 + half);
+            }
+        }
         if (threadIdx.x < p.D) {
             long long pv[3] = {0, 0, 0};
             for (int r = 0; r < p.n_pos; ++r) pv[r] = pos[(size_t)r * p.L + l];
@@ -99,8 +112,10 @@ __device__ __forceinline__ void unrope_qk_body(const __nv_bfloat16* __restrict__
             const __nv_bfloat16* src = second ? p.x2 + (h - p.heads) * p.stride_h2 + l * p.stride_l2 : x + h * p.stride_h + l * p.stride_l;
             __nv_bfloat16* dst = second ? p.out2 + (h - p.heads) * p.out_stride_h2 + l * p.out_stride_l2
                                         : out + h * p.out_stride_h + l * p.out_stride_l;
-            uint4 lo4 = *reinterpret_cast<const uint4*>(src + c0);
-            uint4 hi4 = *reinterpret_cast<const uint4*>(src + c0 + half);
+            if (task != (int)threadIdx.x) {
+                lo4 = *reinterpret_cast<const uint4*>(src + c0);
+                hi4 = *reinterpret_cast<const uint4*>(src + c0 + half);
+            }
             const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(&lo4);
             const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(&hi4);
             uint4 ol4, oh4;
