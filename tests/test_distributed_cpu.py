@@ -82,3 +82,50 @@ def _worker(rank, world, port, sync):
 def test_two_rank_host_logic(sync):
     port = _free_port()
     mp.spawn(_worker, args=(2, port, sync), nprocs=2, join=True)
+
+
+def _runner_worker(rank, world, port):
+    for p in (ROOT, os.path.join(ROOT, "video-retake_b200")):
+        sys.path.insert(0, p)
+    from retake import infer_eval as ie
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        assert ie.shard_indices(7) == [i for i in range(7) if i % world == rank]
+        seen = []
+        merged = ie.run_sharded([10, 11, 12, 13, 14], lambda v: (seen.append(v), v * v)[1], ids="abcde")
+        assert seen == [10 + i for i in range(5) if i % world == rank]            # whole videos, round robin
+        assert merged == {"a": 100, "b": 121, "c": 144, "d": 169, "e": 196}       # same on every rank
+        try:
+            ie.gather_results({"dup": rank})
+            raise AssertionError("a video processed twice must be reported")
+        except RuntimeError:
+            pass
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_whole_video_runner():
+    """reference pattern infer_eval.py:181-205: round-robin shard, one all_gather_object of the results"""
+    port = _free_port()
+    mp.spawn(_runner_worker, args=(2, port), nprocs=2, join=True)
+
+
+def test_frame_sampling_arithmetic():
+    """demo.py:16-25 / dataset_utils.py:39-48 on hand-checked cases"""
+    for p in (ROOT, os.path.join(ROOT, "video-retake_b200")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from retake import infer_eval as ie
+    # 1 h of video extracted at 25 fps, sampled at 2 fps, cap 2048 -> 2048 frames
+    assert ie.get_sample_frames(90000, 2048, 2, 25) == 2048
+    # 100 s at 25 fps sampled at 2 fps -> 200; odd counts round down to even; short clips are capped by their length
+    assert ie.get_sample_frames(2500, 2048, 2, 25) == 200
+    assert ie.get_sample_frames(2513, 2048, 2, 25) == 200 and ie.get_sample_frames(2538, 2048, 2, 25) == 202
+    assert ie.get_sample_frames(7, 2048, 30, 25) == 6
+    idx = ie.get_frame_indices(2500, 2048, 2, 25)
+    assert idx.dtype.name == "int32" and len(idx) == 200 and idx[0] == 0 and idx[-1] == 2499
+    assert idx.tolist()[:4] == [0, 12, 25, 37] and all(b > a for a, b in zip(idx, idx[1:]))
+    # single process: run_sharded degenerates to a plain loop
+    assert ie.run_sharded([1, 2, 3], lambda v: -v) == {0: -1, 1: -2, 2: -3}
+    with pytest.raises(ValueError):
+        ie.shard_indices(4, 2, 2)
