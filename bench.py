@@ -431,8 +431,9 @@ def main():
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                 "achieved_executed": 2 * achieved, "frac_executed": 2 * achieved / peak_tf, "peak_source": peak_src,
                 "ms_per_call": score_ms, "calls_timed": len(timer.pairs),
-                # dram__bytes_read.sum + dram__bytes_write.sum of both launches, profiles/r1_ncu_score_summary.txt (L=4096)
-                "traffic": 67.6e6 if s.L == 4096 else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of both launches per layer (L=4096): batched launches
+                # profiles/r1_ncu_score_batch_summary.txt (1.973 GB / 28 layers), single-layer profiles/r1_ncu_score_summary.txt
+                "traffic": (70.5e6 if s.deferred else 67.6e6) if s.L == 4096 else None,
                 # an exact two-pass softmax needs 2*H*L^2 fp32 ex2; B200 issues 16 MUFU per clock and SM
                 "xu_floor_ms": 2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3,
                 "frac_of_xu_floor": (2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3) / score_ms if score_ms > 0 else 0.0,
