@@ -45,6 +45,20 @@ def test_argument_errors_without_gpu():
     assert lib.rtk_pivot_score_workspace_bytes(28, 4096) == 7 * 28 * 4096 * 4
     assert lib.rtk_pivot_score_workspace_bytes(4, 130) == 7 * 4 * 256 * 4
     assert lib.rtk_pivot_select(a16, 4, 16, None, 17, a16, None, None) == -1   # keep > L
+    # batched update: workspace query, argument errors
+    one = lib.rtk_pivot_update_batch_workspace_bytes(28, 4, 4096, 128, 1)
+    assert lib.rtk_pivot_update_batch_workspace_bytes(28, 4, 4096, 128, 28) > 27 * (one - 1024) > 0
+    assert lib.rtk_pivot_update_batch_workspace_bytes(28, 4, 4096, 128, 64) == lib.rtk_pivot_update_batch_workspace_bytes(28, 4, 4096, 128, 32)
+    assert lib.rtk_pivot_update_batch(None, 2, a16, 1 << 20, None) == -1
+    from retake.longvideo_cache import _UpdateArgs
+    arr = (_UpdateArgs * 2)()
+    a256 = (ctypes.addressof(ctypes.create_string_buffer(1024)) + 255) & ~255
+    assert lib.rtk_pivot_update_batch(arr, 2, a256, 512, None) == -1           # H == 0
+    for x in arr:
+        x.H, x.KVH, x.L, x.D, x.keep = 4, 2, 64, 64, 16
+    assert lib.rtk_pivot_update_batch(arr, 2, a256, 512, None) == -4           # workspace too small
+    arr[0].reforge = 1
+    assert lib.rtk_pivot_update_batch(arr, 2, a256, 1 << 30, None) == -3       # reforge without inv_freq: not batchable
 
 
 def test_host_wrappers_refuse_cpu_tensors():
@@ -70,6 +84,12 @@ def test_build_kvcache_factory():
     assert isinstance(c, PivotKVCache) and isinstance(c, DynamicCache)
     assert c.head_dim == 64 and c.num_key_value_groups == 2 and c.pos_embed_reforge and c.kvcache_compression
     assert c.get_prev_temporal_idx(0) == -1 and c.num_evicted_tokens == [] and c.position_cache == []
+    assert c.deferred_compression is False                 # default: compression inside update(), the reference's call order
+    cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"] = True
+    d = build_kvcache(cfg)
+    assert d.deferred_compression is True and d._deferred == []
+    d.after_forward()                                      # nothing pending: no library call, works without a GPU
+    del cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"]
     cfg.longvideo_kwargs["kvcache_compression_kwargs"]["compression_method"] = "h2o"
     with pytest.raises(NotImplementedError):
         build_kvcache(cfg)

@@ -34,13 +34,14 @@ def make_inputs(T=16, pre=5, post=6):
                 attention_mask=torch.ones(1, ids.numel(), dtype=torch.long).cuda())
 
 
-def lv_kwargs(vis=True, rv=1.0, kv=True, rkv=1.0, reforge=False, chunk_frames=4):
+def lv_kwargs(vis=True, rv=1.0, kv=True, rkv=1.0, reforge=False, chunk_frames=4, deferred=False):
     return {"frame_chunk_size": 8, "chunked_prefill_frames": chunk_frames, "visual_compression": vis,
             "visual_compression_kwargs": {"compression_ratio": rv, "compression_method": "Keyframe", "patch_sync": False,
                                           "return_keyframe_mask": True},
             "kvcache_compression": kv,
             "kvcache_compression_kwargs": {"dynamic_compression_ratio": False, "compression_ratio": rkv,
-                                           "compression_method": "pivotkv", "pos_embed_reforge": reforge}}
+                                           "compression_method": "pivotkv", "pos_embed_reforge": reforge,
+                                           "deferred_compression": deferred}}
 
 
 @pytest.fixture()
@@ -67,6 +68,24 @@ def test_chunked_prefill_without_compression_equals_stock(patched):
         c = model(**inp, use_cache=True).logits[0, -1].float()          # stock transformers forward
         patched.install()
     assert torch.allclose(a, b, atol=0.08, rtol=0.05) and torch.allclose(a, c, atol=0.08, rtol=0.05)
+
+
+def test_deferred_compression_gives_the_same_prefill(patched):
+    """1-D positions (Qwen2 rotary): one batched compression per chunk at after_forward() == compression inside update()"""
+    model = tiny_model()
+    inp = make_inputs()
+    outs = []
+    for deferred in (False, True):
+        model.config.longvideo_kwargs = lv_kwargs(vis=True, rv=0.5, kv=True, rkv=0.5, reforge=True, deferred=deferred)
+        with torch.no_grad():
+            outs.append(model(**inp, use_cache=True))
+    a, b = outs
+    assert b.past_key_values.deferred_compression and not a.past_key_values.deferred_compression
+    assert torch.equal(a.logits, b.logits)
+    for l in range(2):
+        assert torch.equal(a.past_key_values.layers[l].keys, b.past_key_values.layers[l].keys)
+        assert torch.equal(a.past_key_values.layers[l].values, b.past_key_values.layers[l].values)
+        assert torch.equal(a.past_key_values.position_cache[l], b.past_key_values.position_cache[l])
 
 
 @pytest.mark.parametrize("reforge", [False, True])
