@@ -4,8 +4,9 @@ import sys
 
 rows = [json.loads(l) for l in open(sys.argv[1]) if l.strip()]
 print("# Round 1 - kernel sweep on one B200 (BASELINE config 5 + LLaVA-Video shape), `python tools_sweep.py`\n")
-print("Each point is `bench.py --steps 2 --warmup 3` on that configuration (inputs resident in HBM). `score` = one `rtk_pivot_score` call")
-print("(CUDA events inside the timed region), frac = algorithmic flops / measured sustained bf16 peak; `dpselect` = the whole operator,")
+print("Each point is `bench.py --steps 2 --warmup 3` on that configuration (inputs resident in HBM, deferred compression: one batched")
+print("`rtk_pivot_update_batch` per chunk). `score` = the scoring of one layer (CUDA events around the batched scoring of a chunk inside the")
+print("timed region / 28 layers), frac = algorithmic flops / measured sustained bf16 peak; `dpselect` = the whole operator,")
 print("frac = algorithmic bytes / measured HBM peak (small videos are launch/latency dominated: 3 kernels for <= 0.5 GB).\n")
 print("| shape | frames | r_v | r_kv | frames/s | ms/step | score ms (frac) | dpselect ms (frac) |")
 print("|---|---|---|---|---|---|---|---|")

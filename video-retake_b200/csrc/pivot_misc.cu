@@ -78,55 +78,70 @@ __device__ __forceinline__ void rope_table_entry(const RopeParams& p, const floa
 // Reverse rotation of q and k with the tables computed in place (fast path: the rotary module has a static inv_freq):
 // one CTA per token, D threads build the token's cos/sin row in shared memory, then every thread rotates one
 // (head, 8+8 channel) slice of q or k.  Replaces pivot_rope_table_kernel + pivot_rope_kernel of the slow path.
+constexpr int kUnropeTok = 4;      // tokens a CTA un-rotates per step: their rows are all in flight before the first is used
+
 __device__ __forceinline__ void unrope_qk_body(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ pos,
                                                const float* __restrict__ inv_freq, float scaling,
                                                __nv_bfloat16* __restrict__ out, const RopeParams& p) {
-    __shared__ float s_cos[256], s_sin[256];
+    __shared__ float s_cos[kUnropeTok][256], s_sin[kUnropeTok][256];
     const int half = p.D >> 1;
     const int vec_per_row = half >> 3;
     const int ntask = (p.heads + p.heads2) * vec_per_row;
-    for (int l = blockIdx.x; l < p.L; l += gridDim.x) {
-        // the first task's rows are requested before the table is built, so that the trigonometry hides their latency
-        // (at the 7B shape - 32 heads x 8 vectors - a thread has exactly one task)
-        uint4 lo4 = make_uint4(0, 0, 0, 0), hi4 = lo4;
-        {
-            const int task = threadIdx.x;
-            if (task < ntask) {
-                const int v = task % vec_per_row, h = task / vec_per_row;
-                const bool second = h >= p.heads;
-                const __nv_bfloat16* src = second ? p.x2 + (h - p.heads) * p.stride_h2 + l * p.stride_l2 : x + h * p.stride_h + l * p.stride_l;
-                lo4 = *reinterpret_cast<const uint4*>(src + v * 8);
-                hi4 = *reinterpret_cast<const uint4*>(src + v * 8 + half);
+    const int tid = threadIdx.x;
+    // a thread's first task (at the 7B shape - 32 heads x 8 vectors - its only one): same (head, vector) for every token
+    const int v0 = tid % vec_per_row, h0 = tid / vec_per_row;
+    const bool second0 = h0 >= p.heads;
+    const long long src_h0 = second0 ? (long long)(h0 - p.heads) * p.stride_h2 : (long long)h0 * p.stride_h;
+    const long long src_l0 = second0 ? p.stride_l2 : p.stride_l;
+    const __nv_bfloat16* src0 = (second0 ? p.x2 : x) + src_h0 + v0 * 8;
+    for (int l0 = blockIdx.x * kUnropeTok; l0 < p.L; l0 += gridDim.x * kUnropeTok) {
+        const int nl = min(kUnropeTok, p.L - l0);
+        // every row of the step is requested before the tables are built, so that the trigonometry hides the latency
+        uint4 lo4[kUnropeTok], hi4[kUnropeTok];
+        if (tid < ntask) {
+#pragma unroll
+            for (int t = 0; t < kUnropeTok; ++t) {
+                if (t < nl) {
+                    lo4[t] = *reinterpret_cast<const uint4*>(src0 + (l0 + t) * src_l0);
+                    hi4[t] = *reinterpret_cast<const uint4*>(src0 + (l0 + t) * src_l0 + half);
+                }
             }
         }
-        if (threadIdx.x < p.D) {
+        for (int e = tid; e < nl * p.D; e += blockDim.x) {
+            const int t = e / p.D, c = e - t * p.D;
             long long pv[3] = {0, 0, 0};
-            for (int r = 0; r < p.n_pos; ++r) pv[r] = pos[(size_t)r * p.L + l];
-            rope_table_entry(p, inv_freq, pv, threadIdx.x, scaling, s_cos[threadIdx.x], s_sin[threadIdx.x]);
+            for (int r = 0; r < p.n_pos; ++r) pv[r] = pos[(size_t)r * p.L + l0 + t];
+            rope_table_entry(p, inv_freq, pv, c, scaling, s_cos[t][c], s_sin[t][c]);
         }
         __syncthreads();
-        for (int task = threadIdx.x; task < ntask; task += blockDim.x) {
-            const int v = task % vec_per_row, h = task / vec_per_row;
-            const int c0 = v * 8;
-            const bool second = h >= p.heads;
-            const __nv_bfloat16* src = second ? p.x2 + (h - p.heads) * p.stride_h2 + l * p.stride_l2 : x + h * p.stride_h + l * p.stride_l;
-            __nv_bfloat16* dst = second ? p.out2 + (h - p.heads) * p.out_stride_h2 + l * p.out_stride_l2
-                                        : out + h * p.out_stride_h + l * p.out_stride_l;
-            if (task != (int)threadIdx.x) {
-                lo4 = *reinterpret_cast<const uint4*>(src + c0);
-                hi4 = *reinterpret_cast<const uint4*>(src + c0 + half);
-            }
-            const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(&lo4);
-            const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(&hi4);
-            uint4 ol4, oh4;
-            __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(&ol4);
-            __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&oh4);
 #pragma unroll
-            for (int e = 0; e < 8; ++e)
-                rope_rotate_pair(__bfloat162float(xl[e]), __bfloat162float(xh[e]), s_cos[c0 + e], s_sin[c0 + e], s_cos[c0 + half + e],
-                                 s_sin[c0 + half + e], 0, p.inv_scale2, ol[e], oh[e]);
-            *reinterpret_cast<uint4*>(dst + c0) = ol4;
-            *reinterpret_cast<uint4*>(dst + c0 + half) = oh4;
+        for (int t = 0; t < kUnropeTok; ++t) {
+            if (t >= nl) break;
+            const int l = l0 + t;
+            for (int task = tid; task < ntask; task += blockDim.x) {
+                const int v = task % vec_per_row, h = task / vec_per_row;
+                const int c0 = v * 8;
+                const bool second = h >= p.heads;
+                const __nv_bfloat16* src = second ? p.x2 + (h - p.heads) * p.stride_h2 + l * p.stride_l2 : x + h * p.stride_h + l * p.stride_l;
+                __nv_bfloat16* dst = second ? p.out2 + (h - p.heads) * p.out_stride_h2 + l * p.out_stride_l2
+                                            : out + h * p.out_stride_h + l * p.out_stride_l;
+                uint4 a4 = lo4[t], b4 = hi4[t];
+                if (task != tid) {
+                    a4 = *reinterpret_cast<const uint4*>(src + c0);
+                    b4 = *reinterpret_cast<const uint4*>(src + c0 + half);
+                }
+                const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(&a4);
+                const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(&b4);
+                uint4 ol4, oh4;
+                __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(&ol4);
+                __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&oh4);
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    rope_rotate_pair(__bfloat162float(xl[e]), __bfloat162float(xh[e]), s_cos[t][c0 + e], s_sin[t][c0 + e],
+                                     s_cos[t][c0 + half + e], s_sin[t][c0 + half + e], 0, p.inv_scale2, ol[e], oh[e]);
+                *reinterpret_cast<uint4*>(dst + c0) = ol4;
+                *reinterpret_cast<uint4*>(dst + c0 + half) = oh4;
+            }
         }
         __syncthreads();
     }
@@ -722,7 +737,7 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
                 p.bound[i] = acc;
             }
             if (sec && acc != D) return RTK_E_UNSUPPORTED;
-            RTK_LAUNCH_PDL(pivot_unrope_qk_kernel, (unsigned)L, 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)q,
+            RTK_LAUNCH_PDL(pivot_unrope_qk_kernel, (unsigned)((L + kUnropeTok - 1) / kUnropeTok), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)q,
                            (const long long*)a->pos, a->inv_freq, a->attention_scaling, (__nv_bfloat16*)qu, p);
         } else {
             if (!c || !s) return RTK_E_BADARG;
@@ -830,7 +845,7 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
     }
     if (reforge) {
         if (a0.n_pos == 3 && acc != D) return RTK_E_UNSUPPORTED;
-        RTK_LAUNCH_PDL(pivot_unrope_qk_batch_kernel, dim3((unsigned)L, (unsigned)n), 256, 0, st, t, a0.inv_freq,
+        RTK_LAUNCH_PDL(pivot_unrope_qk_batch_kernel, dim3((unsigned)((L + kUnropeTok - 1) / kUnropeTok), (unsigned)n), 256, 0, st, t, a0.inv_freq,
                        a0.attention_scaling, rp);
     }
     if (a0.ev_score_begin) cudaEventRecord((cudaEvent_t)a0.ev_score_begin, st);
