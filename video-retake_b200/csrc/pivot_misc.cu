@@ -78,7 +78,10 @@ __device__ __forceinline__ void rope_table_entry(const RopeParams& p, const floa
 // Reverse rotation of q and k with the tables computed in place (fast path: the rotary module has a static inv_freq):
 // one CTA per token, D threads build the token's cos/sin row in shared memory, then every thread rotates one
 // (head, 8+8 channel) slice of q or k.  Replaces pivot_rope_table_kernel + pivot_rope_kernel of the slow path.
-constexpr int kUnropeTok = 4;      // tokens a CTA un-rotates per step: their rows are all in flight before the first is used
+#ifndef RTK_UNROPE_TOK
+#define RTK_UNROPE_TOK 2     // A/B under ncu, 28 layers x 4096 tokens: 1 -> 597 us, 2 -> 538 us, 4 -> 692 us (100 registers), 8 -> 653 us
+#endif
+constexpr int kUnropeTok = RTK_UNROPE_TOK;      // tokens a CTA un-rotates per step: their rows are all in flight before the first is used
 
 __device__ __forceinline__ void unrope_qk_body(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ pos,
                                                const float* __restrict__ inv_freq, float scaling,
