@@ -24,9 +24,10 @@ for hard in (False, True):
     vc.mallm_compress(xm[None], 4, sync=True, hard=hard)
 for (H, KVH, L, D) in ((4, 2, 130, 64), (28, 4, 200, 128), (8, 8, 1, 128)):
     cfg = types.SimpleNamespace(hidden_size=H * D, num_hidden_layers=2, num_attention_heads=H, num_key_value_heads=KVH)
-    for reforge in (False, True):
+    for reforge, deferred in ((False, False), (True, False), (False, True), (True, True)):
         cfg.longvideo_kwargs = {"kvcache_compression": True, "kvcache_compression_kwargs": {
-            "compression_ratio": 0.3, "compression_method": "pivotkv", "pos_embed_reforge": reforge}}
+            "compression_ratio": 0.3, "compression_method": "pivotkv", "pos_embed_reforge": reforge,
+            "deferred_compression": deferred}}                  # deferred: the batched kernels (rtk_pivot_update_batch)
         cache = lc.PivotKVCache(cfg)
         rot = TableRotary(D)
         rot.inv_freq = rot.inv_freq.cuda()
@@ -40,7 +41,7 @@ for (H, KVH, L, D) in ((4, 2, 130, 64), (28, 4, 200, 128), (8, 8, 1, 128)):
                 pos = torch.stack([chunk * 10 + ar // 16, (ar % 16) // 4, ar % 4])[:, None]
                 cache.keypatches_mask_chunk = (torch.rand(L, generator=g) < 0.3).cuda()
                 cache.update(k, v, layer, {"query_states": q, "position_ids": pos, "rotary_emb": rot, "mrope_section": sec})
-        cache.after_forward()
+            cache.after_forward()
         _ = cache.layers[0].keys.sum().item()
 torch.cuda.synchronize()
 print("sanitize pass done")
