@@ -180,11 +180,14 @@ def test_pivot_update_fuzz(seed):
             assert torch.equal(cache.layers[0].keys, op.rotate(kk[:, :, idx], c2, s2)), tag
 
 
+@pytest.mark.parametrize("deferred", [False, True])
 @pytest.mark.parametrize("seed", range(4))
-def test_cache_state_machine_fuzz(seed):
+def test_cache_state_machine_fuzz(seed, deferred):
     """random interleavings of compressing / plain updates over two layers with ragged chunk lengths, long enough to grow
     the preallocated buffers several times: the cache must always equal [past kept rows | ...] built from the kernel's own
-    kept indices, the returned tensors must equal [past | chunk] (deferred tail overwrite, buffer growth, key_cache views)."""
+    kept indices, the returned tensors must equal [past | chunk] (deferred tail overwrite, buffer growth, key_cache views).
+    ``deferred``: the compression itself is postponed to after_forward() / the layer's next update / the next read and runs
+    batched over the layers that are pending at that moment."""
     from helpers import TableRotary
     from test_gpu_pivotkv import _cfg, _lc, qkv
     lc = _lc()
@@ -193,10 +196,23 @@ def test_cache_state_machine_fuzz(seed):
     ratio = (0.1, 0.3, 0.6, 0.9)[seed]
     rot = TableRotary(D, mrope=False)
     rot.inv_freq = rot.inv_freq.cuda()
-    cache = lc.PivotKVCache(_cfg(H, KVH, D, layers, ratio, False))
+    cfg = _cfg(H, KVH, D, layers, ratio, False)
+    cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"] = deferred
+    cache = lc.PivotKVCache(cfg)
     want_k = [torch.empty(1, KVH, 0, D, dtype=BF, device="cuda") for _ in range(layers)]
     want_v = [torch.empty(1, KVH, 0, D, dtype=BF, device="cuda") for _ in range(layers)]
     evicted = [0] * layers
+    pend = [None] * layers                 # (k, v, kept-index tensor) of a chunk whose kept rows are not folded into want_* yet
+
+    def resolve(layer):
+        if pend[layer] is not None:
+            kk, vv, idx_t = pend[layer]
+            idx = idx_t.long()
+            assert idx.numel() == max(1, int(ratio * kk.shape[2])) and bool((idx[1:] > idx[:-1]).all())
+            want_k[layer] = torch.cat([want_k[layer], kk[:, :, idx]], dim=2)
+            want_v[layer] = torch.cat([want_v[layer], vv[:, :, idx]], dim=2)
+            pend[layer] = None
+
     for step in range(14):
         compress = bool(torch.randint(0, 4, (1,), generator=g))            # 3 of 4 steps compress
         L = int(torch.randint(1, 3000, (1,), generator=g)) if compress else int(torch.randint(1, 40, (1,), generator=g))
@@ -204,28 +220,41 @@ def test_cache_state_machine_fuzz(seed):
         cache.keypatches_mask_chunk = ((torch.rand(L, generator=g) < 0.2).cuda() if (compress and step % 2) else None)
         for layer in range(layers):
             q, k, v = qkv(H, KVH, L, D, 1.0, seed=seed * 1000 + step * 10 + layer)
-            pos = (want_k[layer].shape[2] + torch.arange(L))[None].cuda()
+            past_len = cache.get_seq_length(layer)
+            pos = (past_len + torch.arange(L))[None].cuda()
             kw = {"position_ids": pos}
             if compress:
                 kw.update({"query_states": q, "rotary_emb": rot, "mrope_section": None})
             ko, vo = cache.update(k, v, layer, kw)
+            resolve(layer)                 # update() settles this layer's own debt before it appends
+            assert want_k[layer].shape[2] == past_len
             assert torch.equal(ko, torch.cat([want_k[layer], k], dim=2)) and torch.equal(vo, torch.cat([want_v[layer], v], dim=2))
             if compress:
-                idx = cache.last_keep_indices.long()
-                assert idx.numel() == max(1, int(ratio * L))
-                want_k[layer] = torch.cat([want_k[layer], k[:, :, idx]], dim=2)
-                want_v[layer] = torch.cat([want_v[layer], v[:, :, idx]], dim=2)
-                evicted[layer] += L - idx.numel()
+                if deferred:
+                    assert cache._deferred and cache.layers[layer]._deferred_owner is cache
+                    pend[layer] = (k, v, cache._deferred[-1]["outs"]["keep_idx"])
+                else:
+                    pend[layer] = (k, v, cache.last_keep_indices)
+                    resolve(layer)
+                evicted[layer] += L - max(1, int(ratio * L))
             else:
                 want_k[layer] = torch.cat([want_k[layer], k], dim=2)
                 want_v[layer] = torch.cat([want_v[layer], v], dim=2)
         if step % 3 == 2:
             cache.after_forward()
+            assert not cache._deferred
+            for layer in range(layers):
+                resolve(layer)
         for layer in range(layers):
-            assert cache.get_seq_length(layer) == want_k[layer].shape[2]
+            keep_pending = 0 if pend[layer] is None else pend[layer][2].numel()
+            assert cache.get_seq_length(layer) == want_k[layer].shape[2] + keep_pending      # lengths are settled at once
             if step % 2:
-                assert torch.equal(cache.layers[layer].keys, want_k[layer]) and torch.equal(cache.key_cache[layer], want_k[layer])
+                got_k = cache.layers[layer].keys                                             # a read settles the bytes
+                resolve(layer)
+                assert torch.equal(got_k, want_k[layer]) and torch.equal(cache.key_cache[layer], want_k[layer])
                 assert torch.equal(cache.layers[layer].values, want_v[layer])
     for layer in range(layers):
-        assert torch.equal(cache.layers[layer].keys, want_k[layer]) and torch.equal(cache.layers[layer].values, want_v[layer])
+        got_k = cache.layers[layer].keys
+        resolve(layer)
+        assert torch.equal(got_k, want_k[layer]) and torch.equal(cache.layers[layer].values, want_v[layer])
         assert cache.num_evicted_tokens[layer] == evicted[layer]
