@@ -439,7 +439,9 @@ def main():
                 "frac_of_xu_floor": (2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3) / score_ms if score_ms > 0 else 0.0,
                 "note": ("algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it twice and is bounded by "
                          "MUFU.EX2 throughput and the softmax warps' instruction stream (XU pipe 73-76 % busy; xu_floor_ms = "
-                         "2*H*L^2 exps at 16/clk/SM, 1.9 GHz), not by the tensor pipe (36 % busy) - DESIGN.md section 5")}
+                         "2*H*L^2 exps at 16/clk/SM, 1.9 GHz), not by the tensor pipe (36 % busy); the kernel also holds the board at its "
+                         "1 kW power cap (clocks.reasons sw_power_cap; profiles/r1_score_power_probe.json: the TMA + MMA feeder alone "
+                         "needs 0.245 ms per call at 1 kW) - DESIGN.md section 5")}
     dps_ms = sum(a.elapsed_time(b) for a, b in timer.dpselect) / max(1, len(timer.dpselect))
     hbm = peaks.get("hbm_gbs", 6650.0)
     dps_bytes = 2.0 * s.T * s.N * s.C + 4.0 * s.T * s.N + 4.0 * s.t * s.N * s.C
