@@ -83,14 +83,44 @@ __device__ __forceinline__ void rope_table_entry(const RopeParams& p, const floa
 #endif
 constexpr int kUnropeTok = RTK_UNROPE_TOK;      // tokens a CTA un-rotates per step: their rows are all in flight before the first is used
 
+// packed bf16 arithmetic with ONE rounding per operation.  The reference's chain rounds every product and every
+// difference to bf16 after computing it in fp32; for bf16 operands (p = 8 bits) the fp32 intermediate (24 >= 2p + 2 bits)
+// makes that double rounding innocuous, so mul / add / sub.rn.bf16x2 return the same bits with a quarter of the instructions.
+__device__ __forceinline__ uint32_t sub_bf16x2_rn(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("sub.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t add_bf16x2_rn(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+// reverse rotation of two channel pairs: xa = channels (c, c+1) of the lower half, xb = their partners (c + D/2, ...);
+// cos / sin of the lower-half channels (the upper half uses the same values, see unrope_qk_body)
+__device__ __forceinline__ void unrotate_bf16x2(uint32_t xa, uint32_t xb, uint32_t cs, uint32_t sn, bool scale, float inv_scale2,
+                                                uint32_t& oa, uint32_t& ob) {
+    const uint32_t ta = mul_bf16x2_rn(xa, cs), ra = mul_bf16x2_rn(xb ^ 0x80008000u, sn);     // rotate_half: -x[c + D/2]
+    const uint32_t tb = mul_bf16x2_rn(xb, cs), rb = mul_bf16x2_rn(xa, sn);
+    oa = sub_bf16x2_rn(ta, ra);
+    ob = sub_bf16x2_rn(tb, rb);
+    if (scale) {
+        oa = scale_bf16x2_rn(oa, inv_scale2);
+        ob = scale_bf16x2_rn(ob, inv_scale2);
+    }
+}
+
 __device__ __forceinline__ void unrope_qk_body(const __nv_bfloat16* __restrict__ x, const long long* __restrict__ pos,
                                                const float* __restrict__ inv_freq, float scaling,
                                                __nv_bfloat16* __restrict__ out, const RopeParams& p) {
-    __shared__ float s_cos[kUnropeTok][256], s_sin[kUnropeTok][256];
+    // cos / sin rows of the step's tokens, LOWER half of the channels only: emb = cat(freqs, freqs) and the mrope blocks
+    // i and i + 3 read the same position row (sections sum to D / 2), so channel c + D/2 has the tables of channel c
+    __shared__ __align__(16) __nv_bfloat16 s_cos[kUnropeTok][128], s_sin[kUnropeTok][128];
     const int half = p.D >> 1;
     const int vec_per_row = half >> 3;
     const int ntask = (p.heads + p.heads2) * vec_per_row;
     const int tid = threadIdx.x;
+    const bool scale = p.inv_scale2 != 1.0f;
     // a thread's first task (at the 7B shape - 32 heads x 8 vectors - its only one): same (head, vector) for every token
     const int v0 = tid % vec_per_row, h0 = tid / vec_per_row;
     const bool second0 = h0 >= p.heads;
@@ -110,11 +140,14 @@ __device__ __forceinline__ void unrope_qk_body(const __nv_bfloat16* __restrict__
                 }
             }
         }
-        for (int e = tid; e < nl * p.D; e += blockDim.x) {
-            const int t = e / p.D, c = e - t * p.D;
+        for (int e = tid; e < nl * half; e += blockDim.x) {
+            const int t = e / half, c = e - t * half;
             long long pv[3] = {0, 0, 0};
             for (int r = 0; r < p.n_pos; ++r) pv[r] = pos[(size_t)r * p.L + l0 + t];
-            rope_table_entry(p, inv_freq, pv, c, scaling, s_cos[t][c], s_sin[t][c]);
+            float co, si;
+            rope_table_entry(p, inv_freq, pv, c, scaling, co, si);
+            s_cos[t][c] = __float2bfloat16_rn(co);          // exact: the entries are bf16 values already
+            s_sin[t][c] = __float2bfloat16_rn(si);
         }
         __syncthreads();
 #pragma unroll
@@ -133,15 +166,13 @@ __device__ __forceinline__ void unrope_qk_body(const __nv_bfloat16* __restrict__
                     a4 = *reinterpret_cast<const uint4*>(src + c0);
                     b4 = *reinterpret_cast<const uint4*>(src + c0 + half);
                 }
-                const __nv_bfloat16* xl = reinterpret_cast<const __nv_bfloat16*>(&a4);
-                const __nv_bfloat16* xh = reinterpret_cast<const __nv_bfloat16*>(&b4);
+                const uint4 cs = *reinterpret_cast<const uint4*>(&s_cos[t][c0]);
+                const uint4 sn = *reinterpret_cast<const uint4*>(&s_sin[t][c0]);
                 uint4 ol4, oh4;
-                __nv_bfloat16* ol = reinterpret_cast<__nv_bfloat16*>(&ol4);
-                __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&oh4);
-#pragma unroll
-                for (int e = 0; e < 8; ++e)
-                    rope_rotate_pair(__bfloat162float(xl[e]), __bfloat162float(xh[e]), s_cos[t][c0 + e], s_sin[t][c0 + e],
-                                     s_cos[t][c0 + half + e], s_sin[t][c0 + half + e], 0, p.inv_scale2, ol[e], oh[e]);
+                unrotate_bf16x2(a4.x, b4.x, cs.x, sn.x, scale, p.inv_scale2, ol4.x, oh4.x);
+                unrotate_bf16x2(a4.y, b4.y, cs.y, sn.y, scale, p.inv_scale2, ol4.y, oh4.y);
+                unrotate_bf16x2(a4.z, b4.z, cs.z, sn.z, scale, p.inv_scale2, ol4.z, oh4.z);
+                unrotate_bf16x2(a4.w, b4.w, cs.w, sn.w, scale, p.inv_scale2, ol4.w, oh4.w);
                 *reinterpret_cast<uint4*>(dst + c0) = ol4;
                 *reinterpret_cast<uint4*>(dst + c0 + half) = oh4;
             }
@@ -799,11 +830,20 @@ extern "C" size_t rtk_pivot_update_batch_workspace_bytes(int64_t H, int64_t KVH,
            n * (align256((size_t)H * L * D * 2) + align256((size_t)KVH * L * D * 2)) + align256(n * sizeof(long long)) + 256;
 }
 
+#ifndef RTK_UNROT_TOKEN_MAJOR
+#define RTK_UNROT_TOKEN_MAJOR 1     // batched path: un-rotated copies laid out [L, heads, D] like the attention's own tensors
+#endif
+
 // one group of <= kMaxBatchLayers layers
 static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, cudaStream_t st) {
     const rtk_pivot_update_args& a0 = a[0];
     const int64_t H = a0.H, KVH = a0.KVH, L = a0.L, D = a0.D;
     const bool reforge = a0.reforge != 0;
+    // Layout of the un-rotated Q / K copies.  With 28 layers they are 1 GB and go through HBM: token-major rows make every
+    // CTA of the un-rotation kernel write one contiguous block (all heads of its tokens) instead of one 256-byte row per
+    // head 1 MB apart; the scoring kernels take any (head, token) strides through their tensor maps.
+    const int64_t uq_sh = RTK_UNROT_TOKEN_MAJOR ? D : L * D, uq_sl = RTK_UNROT_TOKEN_MAJOR ? H * D : D;
+    const int64_t uk_sh = RTK_UNROT_TOKEN_MAJOR ? D : L * D, uk_sl = RTK_UNROT_TOKEN_MAJOR ? KVH * D : D;
     void* score_ws = ws;                ws += align256(rtk_pivot_score_workspace_bytes(H * n, L));
     char* qu0 = ws;                     ws += (size_t)n * align256((size_t)H * L * D * 2);
     char* ku0 = ws;                     ws += (size_t)n * align256((size_t)KVH * L * D * 2);
@@ -820,8 +860,8 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
         t.k_in[i] = (const __nv_bfloat16*)x.k;    t.kin_stride_h[i] = x.k_stride_h;   t.kin_stride_l[i] = x.k_stride_l;
         t.qu[i] = (__nv_bfloat16*)qu;             t.ku[i] = (__nv_bfloat16*)ku;
         t.k[i] = reforge ? (const __nv_bfloat16*)ku : (const __nv_bfloat16*)x.k;
-        t.k_stride_h[i] = reforge ? L * D : x.k_stride_h;
-        t.k_stride_l[i] = reforge ? D : x.k_stride_l;
+        t.k_stride_h[i] = reforge ? uk_sh : x.k_stride_h;
+        t.k_stride_l[i] = reforge ? uk_sl : x.k_stride_l;
         t.v[i] = (const __nv_bfloat16*)x.v;       t.v_stride_h[i] = x.v_stride_h;     t.v_stride_l[i] = x.v_stride_l;
         t.pos[i] = (const long long*)x.pos;       t.keymask[i] = x.keymask;
         t.k_out[i] = (__nv_bfloat16*)x.k_out;     t.v_out[i] = (__nv_bfloat16*)x.v_out;
@@ -831,15 +871,15 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
         if (i < n) {
             sb.q[i] = reforge ? (const void*)qu : x.q;
             sb.k[i] = reforge ? (const void*)ku : x.k;
-            sb.q_stride_h[i] = reforge ? L * D : x.q_stride_h;   sb.q_stride_l[i] = reforge ? D : x.q_stride_l;
-            sb.k_stride_h[i] = reforge ? L * D : x.k_stride_h;   sb.k_stride_l[i] = reforge ? D : x.k_stride_l;
+            sb.q_stride_h[i] = reforge ? uq_sh : x.q_stride_h;   sb.q_stride_l[i] = reforge ? uq_sl : x.q_stride_l;
+            sb.k_stride_h[i] = reforge ? uk_sh : x.k_stride_h;   sb.k_stride_l[i] = reforge ? uk_sl : x.k_stride_l;
             sb.head_scores[i] = x.head_scores;
         }
     }
     RopeParams rp = {};
     rp.heads = (int)H; rp.L = (int)L; rp.D = (int)D; rp.n_pos = a0.n_pos; rp.forward = 0;
-    rp.out_stride_h = L * D; rp.out_stride_l = D;
-    rp.heads2 = (int)KVH; rp.out_stride_h2 = L * D; rp.out_stride_l2 = D;
+    rp.out_stride_h = uq_sh; rp.out_stride_l = uq_sl;
+    rp.heads2 = (int)KVH; rp.out_stride_h2 = uk_sh; rp.out_stride_l2 = uk_sl;
     rp.inv_scale2 = a0.inv_scale2;
     int acc = 0;
     for (int i = 0; i < 6; ++i) {
