@@ -350,12 +350,16 @@ def main():
     launches0 = _native.launch_count()
     timer.on = True
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    marks = []
     e0.record()
     for _ in range(a.steps):
         res = run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer)
+        marks.append(torch.cuda.Event(enable_timing=True))
+        marks[-1].record()
     e1.record()
     sync_all()
     timer.on = False
+    per_step = [p0.elapsed_time(p1) for p0, p1 in zip([e0] + marks[:-1], marks)]       # this rank's steps, device time
     launches = _native.launch_count() - launches0
     clocks = clocks_summary(sampler)
     ms = e0.elapsed_time(e1)
@@ -453,7 +457,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": config, "roofline": roofline, "roofline_dpselect": dpselect_roofline,
-            "gpu_launches": int(launches)}
+            "gpu_launches": int(launches),
+            "step_ms": {"median": sorted(per_step)[len(per_step) // 2], "min": min(per_step), "max": max(per_step)}}
     if e2e is not None:
         line["e2e"] = e2e
     if clocks is not None:
