@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--layers", type=int, default=28)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-immediate-ab", action="store_true", help="skip the extra timing with deferred compression off")
     return ap.parse_args()
 
 
@@ -370,6 +371,29 @@ def main():
     ms_per_step = ms / a.steps
     value = world * s.frames / (ms_per_step * 1e-3)
 
+    # ---- A/B inside the same process: the reference's call order (compression inside every update(), one rtk_pivot_update
+    #      per layer) on the same inputs; reported next to `value`, never instead of it
+    immediate = None
+    if s.deferred and not a.no_immediate_ab:
+        import copy
+        s_imm = copy.copy(s)
+        s_imm.deferred = False
+        run_step(s_imm, x, q, k, v, rotary, lc, vc, pos_grid)
+        sync_all()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        for _ in range(a.steps):
+            run_step(s_imm, x, q, k, v, rotary, lc, vc, pos_grid)
+        i1.record()
+        sync_all()
+        ims = i0.elapsed_time(i1)
+        if dist is not None:
+            t = torch.tensor([ims], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ims = float(t)
+        immediate = {"value": world * s.frames / (ims / a.steps * 1e-3), "unit": UNIT, "ms_per_step": ims / a.steps,
+                     "what": "deferred_compression off: compression inside every update(), bit-identical results"}
+
     # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region
     e2e = None
     if not a.no_e2e:
@@ -459,6 +483,8 @@ def main():
             "data": "synthetic", "config": config, "roofline": roofline, "roofline_dpselect": dpselect_roofline,
             "gpu_launches": int(launches),
             "step_ms": {"median": sorted(per_step)[len(per_step) // 2], "min": min(per_step), "max": max(per_step)}}
+    if immediate is not None:
+        line["immediate_compression"] = immediate
     if e2e is not None:
         line["e2e"] = e2e
     if clocks is not None:

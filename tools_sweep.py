@@ -19,7 +19,7 @@ os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 with open(os.path.join(ROOT, "gpurun_out", "sweep.jsonl"), "w") as out:
     for shape, frames, rv, rkv in points:
         cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--shape", shape, "--frames", str(frames), "--visual-ratio", str(rv),
-               "--kv-ratio", str(rkv), "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-e2e"]
+               "--kv-ratio", str(rkv), "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-e2e", "--no-immediate-ab"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         line = [l for l in r.stdout.splitlines() if l.startswith("{")]
         if not line:
