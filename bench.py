@@ -417,6 +417,7 @@ def main():
             ev.record()
         e0.record()
         d2h = 0
+        results = []
         enqueue_copy(0)
         for i in range(a.steps):
             if i + 1 < a.steps:
@@ -425,10 +426,15 @@ def main():
             xd, qd, kd, vd = bufs[i % 2]
             keep_idx, seq = run_step(s, xd, qd, kd, vd, rotary, lc, vc, pos_grid)
             freed[i % 2].record()
-            back = keep_idx.cpu()
+            # the step's result goes back to pinned host memory on the compute stream, without stalling the host: the copy
+            # is ordered before e1, so every step's read-back completes inside the timed region
+            back = torch.empty(keep_idx.shape, dtype=keep_idx.dtype, pin_memory=True)
+            back.copy_(keep_idx, non_blocking=True)
+            results.append(back)
             d2h = back.numel() * back.element_size()
         e1.record()
         sync_all()
+        assert all(1 <= int(r.numel()) <= s.keep and 0 <= int(r[-1]) < s.L for r in results)       # the read-backs really arrived
         ems = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ems], device=dev)
