@@ -35,9 +35,14 @@ namespace rtk {
 
 constexpr int kTile = 128;            // rows of both operand tiles, = UMMA M = UMMA N
 constexpr int kHeadDim = 128;         // largest D: two 64-element swizzle atoms (D = 64 uses one)
+#ifndef RTK_SCORE_PAIR
+#define RTK_SCORE_PAIR 1              // 1 (default): a unit keeps TWO stationary tiles and every streamed tile feeds two MMAs - half
+#endif                                //    the L2 -> shared-memory traffic per flop (profiles/r1_mma_energy_probe.txt: ~35-40 pJ per
+                                      //    byte).  Same box, sustained: 0.3363 -> 0.3207 ms per layer, 3070 -> 3202 frames/s.  0: one tile.
 #ifndef RTK_SCORE_STAGES
-#define RTK_SCORE_STAGES 4            // streamed-operand ring depth
+#define RTK_SCORE_STAGES (RTK_SCORE_PAIR ? 2 : 4)   // streamed-operand ring depth (a paired stage lasts two MMAs)
 #endif
+constexpr int kPair = RTK_SCORE_PAIR ? 2 : 1;   // stationary tiles per unit
 constexpr int kStages = RTK_SCORE_STAGES;
 #ifndef RTK_SCORE_ASLOTS
 #define RTK_SCORE_ASLOTS 2            // stationary-tile slots: 2 = the next unit's tile is fetched while this unit still computes
@@ -60,8 +65,8 @@ constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] sw
 
 struct ScoreSmem {
     // offsets inside dynamic shared memory (1024-byte aligned base)
-    static constexpr uint32_t a_tile = 0;                                             // [kASlots] stationary tiles
-    static constexpr uint32_t b_ring = kASlots * kTileBytes;
+    static constexpr uint32_t a_tile = 0;                                             // [kASlots][kPair] stationary tiles
+    static constexpr uint32_t b_ring = kASlots * kPair * kTileBytes;
     static constexpr uint32_t stats = b_ring + kStages * kTileBytes;                 // [kStatSlots][128] f32
     static constexpr uint32_t merge = stats + kStatSlots * kTile * 4;                // [4][128][2] f32
     static constexpr uint32_t bars = merge + 8 * kTile * 2 * 4;          // up to 8 groups
@@ -408,14 +413,14 @@ struct TileRange {
         }
 #endif
     }
-    // H: heads of all layers, Hl: heads per layer
+    // H: heads of all layers, Hl: heads per layer; a head has ceil(nt / kPair) units of kPair stationary tiles
     __device__ __forceinline__ TileRange(int H, int Hl, int nt_) : nt(nt_), layer(0) {
         n_layers = H / Hl;
-        units_per_layer = Hl * nt_;
+        units_per_layer = Hl * ((nt_ + kPair - 1) / kPair);
         Gl = (long long)units_per_layer * nt_;
         set_layer_range();
     }
-    // u: unit index over all layers (= head-of-all-layers * nt + stationary tile)
+    // u: unit index over all layers (= head-of-all-layers * units per head + stationary tile (pair))
     __device__ __forceinline__ bool next(int& u, int& tb0, int& tb1) {
         while (g >= g1) {
             if (++layer >= n_layers) return false;
@@ -493,7 +498,8 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
         if (lane == 0) {
             uint32_t cnt = 0, ucnt = 0;
             while (range.next(u, tb0, tb1)) {
-                const int hh = u / nt, ta = u - hh * nt;             // hh: head index over all layers of the launch
+                const int nta = (nt + kPair - 1) / kPair;            // units per head
+                const int hh = u / nta, ta = (u - hh * nta) * kPair; // hh: head index over all layers of the launch; first stationary tile
                 const int layer = (NL == 1) ? 0 : hh / prm.Hl;
                 const int h = hh - layer * prm.Hl;
                 const CUtensorMap* a_map = a_maps + layer;
@@ -504,12 +510,15 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                 // MMAs of the previous unit are still running (no pipeline bubble at unit boundaries)
                 const int as = ucnt % kASlots;
                 mbar_wait_feeder(a_empty(as), ((ucnt / kASlots) & 1u) ^ 1u);
-                mbar_arrive_expect_tx(a_full(as), prm.n_atoms * kHalfBytes);
-                for (int kk = 0; kk < prm.n_atoms; ++kk) {
-                    const int row = ta * kTile;
-                    tma_load_3d(base + ScoreSmem::a_tile + as * kTileBytes + kk * kHalfBytes, a_map, kk * 64, a_l1 ? row : a_head,
-                                a_l1 ? a_head : row, a_full(as));
-                }
+                mbar_arrive_expect_tx(a_full(as), kPair * prm.n_atoms * kHalfBytes);
+                for (int pa = 0; pa < kPair; ++pa)
+                    for (int kk = 0; kk < prm.n_atoms; ++kk) {
+                        // (an odd tile count leaves the last unit one tile short: its second slot repeats the first, the
+                        //  softmax side drops that result)
+                        const int row = ((ta + pa < nt) ? ta + pa : ta) * kTile;
+                        tma_load_3d(base + ScoreSmem::a_tile + (as * kPair + pa) * kTileBytes + kk * kHalfBytes, a_map, kk * 64,
+                                    a_l1 ? row : a_head, a_l1 ? a_head : row, a_full(as));
+                    }
                 ++ucnt;
                 for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                     const int s = cnt % kStages;
@@ -539,6 +548,34 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
             const int as = ucnt % kASlots;
             mbar_wait_feeder(a_full(as), (ucnt / kASlots) & 1u);
             ++ucnt;
+#if RTK_SCORE_PAIR
+            // streamed tile cnt feeds both stationary tiles: accumulators 2*(cnt&1) (tile 0) and 2*(cnt&1)+1 (tile 1)
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                const int s = cnt % kStages, bp = 2 * (int)(cnt & 1u);
+                mbar_wait_feeder(b_full(s), (cnt / kStages) & 1u);
+                mbar_wait_feeder(t_empty(bp), ((cnt >> 1) & 1u) ^ 1u);
+                mbar_wait_feeder(t_empty(bp + 1), ((cnt >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t b0 = base + ScoreSmem::b_ring + s * kTileBytes;
+                    const int nks = prm.n_atoms * 4;
+#pragma unroll
+                    for (int pa = 0; pa < 2; ++pa) {
+                        const uint32_t a0 = base + ScoreSmem::a_tile + (as * 2 + pa) * kTileBytes;
+#pragma unroll 8
+                        for (int ks = 0; ks < nks; ++ks) {
+                            const uint32_t off = (ks >> 2) * kHalfBytes + (ks & 3) * 32;
+                            umma_bf16(tmem_base + (bp + pa) * kTile, umma_desc_sw128(a0 + off), umma_desc_sw128(b0 + off), kIdesc,
+                                      ks > 0 ? 1u : 0u);
+                        }
+                        tc_commit(t_full(bp + pa));
+                    }
+                    tc_commit(b_empty(s));
+                    if (tb == tb1 - 1) tc_commit(a_empty(as));
+                }
+                __syncwarp();
+            }
+#else
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 const int s = cnt % kStages, b = cnt % kAccBufs;
                 mbar_wait_feeder(b_full(s), (cnt / kStages) & 1u);
@@ -559,6 +596,7 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                 }
                 __syncwarp();
             }
+#endif
         }
     } else {
         // ================================== softmax: 4 groups x 4 warps; tile n -> groups 2*(n&1), 2*(n&1)+1 (column halves)
@@ -573,9 +611,35 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
         const uint64_t inv2 = pk2(inv, inv), l2e2 = pk2(kLog2e, kLog2e);
         uint32_t cnt = 0;
         while (range.next(u, tb0, tb1)) {
+#if RTK_SCORE_PAIR
+            // groups 0, 1 serve the unit's first stationary tile, groups 2, 3 its second one (64-column halves each)
+            const int nta = (nt + 1) / 2;
+            const int h = u / nta, ta = (u - h * nta) * 2 + (grp >> 1);
+            const bool has_tile = ta < nt;           // odd tile count: the last unit's second tile is a repeat, dropped below
+#else
             const int h = u / nt, ta = u - h * nt;
+            const bool has_tile = true;
+#endif
             SoftmaxState st;
-#if RTK_SCORE_GROUPS
+#if RTK_SCORE_PAIR
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                const int b = 2 * (int)(cnt & 1u) + (grp >> 1);
+                mbar_wait(t_full(b), (cnt >> 1) & 1u);
+                tc_fence_after();
+                if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
+                const int valid = prm.L - tb * kTile - half * 64;      // streamed rows of this half that exist
+                const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + half * 64;
+                {
+                    uint32_t r[64];
+                    tmem_ld64(lane_addr + b * kTile, r);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 64>(r, 0, valid, st, cq, inv, inv2, l2e2);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty(b));
+            }
+#elif RTK_SCORE_GROUPS
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 const int b = cnt % kAccBufs;
                 bool waited = false;
@@ -743,17 +807,18 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
             const int part = (tb0 == 0) ? 0 : 1;
             const bool whole = (tb0 == 0) && (tb1 == nt);
             const size_t o = (size_t)h * nt * kTile + (size_t)ta * kTile + row;
+            // groups that fold into one row of one stationary tile: all of them, or (paired units) the two column halves
+            const int g_lo = RTK_SCORE_PAIR ? (grp & ~1) : 0, g_hi = RTK_SCORE_PAIR ? g_lo + 2 : kGroups;
+            const bool folder = (grp == g_lo) && has_tile;
             if (PASS == 1) {
                 merge[(grp * kTile + row) * 2] = m;
                 merge[(grp * kTile + row) * 2 + 1] = a0 + a1;
                 asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
-                if (grp == 0) {
+                if (folder) {
                     float mn = -INFINITY;
-#pragma unroll
-                    for (int g = 0; g < kGroups; ++g) mn = fmaxf(mn, merge[(g * kTile + row) * 2]);
+                    for (int g = g_lo; g < g_hi; ++g) mn = fmaxf(mn, merge[(g * kTile + row) * 2]);
                     float lt = 0.f;
-#pragma unroll
-                    for (int g = 0; g < kGroups; ++g) {
+                    for (int g = g_lo; g < g_hi; ++g) {
                         const float mg = merge[(g * kTile + row) * 2];
                         if (mg > -INFINITY) lt += merge[(g * kTile + row) * 2 + 1] * ex2f((mg - mn) * kLog2e);
                     }
@@ -764,10 +829,9 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
             } else {
                 merge[grp * kTile + row] = a0 + a1;
                 asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
-                if (grp == 0) {
-                    float cs = merge[row];
-#pragma unroll
-                    for (int g = 1; g < kGroups; ++g) cs += merge[g * kTile + row];
+                if (folder) {
+                    float cs = merge[g_lo * kTile + row];
+                    for (int g = g_lo + 1; g < g_hi; ++g) cs += merge[g * kTile + row];
                     prm.colsum_part[(size_t)part * hl + o] = cs;
                     if (whole) prm.colsum_part[hl + o] = 0.f;
                 }
@@ -883,7 +947,7 @@ static int score_launch(const ScoreBatch& b, ScoreParams prm, cudaStream_t st) {
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int units = prm.Hl * prm.nt;                 // per layer: the grid (and so every cut point) is that of one layer
+    const int units = prm.Hl * ((prm.nt + kPair - 1) / kPair);   // per layer: the grid (and so every cut point) is that of one layer
     const int grid = units < sms ? units : sms;
     const size_t smem = ScoreSmem::total + 1024;
     cudaError_t e = cudaFuncSetAttribute(pivot_score_kernel<1, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
