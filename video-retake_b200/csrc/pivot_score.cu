@@ -6,14 +6,18 @@
 // Column sums of a row-normalised softmax need the row statistics first, so the contraction runs twice:
 //   pass 1 (rows = queries)  D = Q_tile . K_tile^T : per query row the running max / sum  -> c_q = m*log2e + log2(l)
 //   pass 2 (rows = keys)     D = K_tile . Q_tile^T : p = bf16(exp2(s*log2e - c_q)), accumulated per key row
-// In both passes a CTA keeps one 128-row "stationary" tile in shared memory and streams the other operand
-// through a 4-stage TMA ring; accumulators are 128x128 fp32 tiles in TMEM (4 buffers = all 512 columns).
+// In both passes a CTA keeps a PAIR of 128-row "stationary" tiles in shared memory (two slots of two tiles: the next
+// unit's pair is prefetched) and streams the other operand through a 2-stage TMA ring; every streamed tile feeds two
+// MMAs, one per stationary tile, which halves the L2 -> shared-memory traffic per flop - the kernel runs at the board's
+// power cap and that traffic is a quarter of the budget.  Accumulators are 128x128 fp32 tiles in
+// TMEM (4 buffers = all 512 columns: two streamed tiles x two stationary tiles).
 // Because the softmax side owns whole TMEM lanes, pass 1 reduces along columns inside a thread (no shuffles)
 // and pass 2 accumulates the column sums inside a thread as well - hence the transposed second pass.
 //
 // Warp roles (576 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane), warps 2-17
-// four softmax groups of four warps (one warp per TMEM lane quarter): accumulator tile n goes to groups 2(n&1) and
-// 2(n&1)+1, each taking 64 of its 128 columns with one tcgen05.ld.32x32b.x64.  Per logit the softmax side issues two
+// four softmax groups of four warps (one warp per TMEM lane quarter): groups 0, 1 serve the accumulators of the first
+// stationary tile, groups 2, 3 those of the second, each taking 64 of the 128 columns with one tcgen05.ld.32x32b.x64
+// (-DRTK_SCORE_PAIR=0: one stationary tile per unit, 4-stage ring, accumulator tile n -> groups 2(n&1), 2(n&1)+1).  Per logit the softmax side issues two
 // in-place fp32->bf16 roundings (F2FP with a zero low half), packed f32x2 scale / FMA / add, one MUFU.EX2 and (pass 1)
 // half an FMNMX3; what bounds it is the MUFU pipe and the softmax warps' issue slots (profiles/r1_score_ab_experiments.md).
 // Every -DRTK_SCORE_* flag below is an A/B switch documented there; the defaults are the shipped configuration.
