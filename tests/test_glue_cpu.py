@@ -64,3 +64,55 @@ def test_llava_helpers():
     assert g.retake_LlavaOnevisionForConditionalGeneration_get_chunk_size(me, me.config, px) == 32 * 14 * 14   # 6272
     ids = torch.tensor([[9, 9, 1, 2]])
     assert g.retake_LlavaOnevisionForConditionalGeneration_segment_input_ids(me, ids) == [(0, 2, "video"), (2, 4, "text")]
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Work partition of the scoring kernels (csrc/pivot_score.cu, struct TileRange) restated in Python: the invariants the
+# kernel's partial-result protocol relies on, over the shapes the tests and the benchmark use.
+def _tile_ranges(heads_per_layer, nt, layers, grid, pair):
+    """[(cta, layer, unit, tb0, tb1)] in the order a CTA walks them (TileRange::next)"""
+    nta = (nt + pair - 1) // pair
+    units_per_layer = heads_per_layer * nta
+    Gl = units_per_layer * nt
+    out = []
+    for cta in range(grid):
+        for layer in range(layers):
+            g, g1 = Gl * cta // grid, Gl * (cta + 1) // grid
+            while g < g1:
+                ul = g // nt
+                tb0 = g - ul * nt
+                tb1 = min(nt, tb0 + (g1 - g))
+                out.append((cta, layer, layer * units_per_layer + ul, tb0, tb1))
+                g += tb1 - tb0
+    return out, units_per_layer
+
+
+def test_score_kernel_partition_invariants():
+    import itertools
+    for (H, nt, layers), pair in itertools.product([(28, 32, 1), (28, 32, 28), (28, 49, 3), (4, 8, 2), (4, 1, 5), (14, 1, 1), (8, 2, 33),
+                                                    (28, 18, 2), (2, 3, 1)], (1, 2)):
+        nta = (nt + pair - 1) // pair
+        grid = min(H * nta, 148)                       # host side: one layer's units decide the grid
+        steps, upl = _tile_ranges(H, nt, layers, grid, pair)
+        seen = {}
+        for cta, layer, u, tb0, tb1 in steps:
+            assert 0 <= tb0 < tb1 <= nt and layer * upl <= u < (layer + 1) * upl
+            seen.setdefault(u, []).append((cta, tb0, tb1))
+        assert sorted(seen) == list(range(layers * upl)), "every unit of every layer is visited"
+        for u, parts in seen.items():
+            parts.sort(key=lambda p: p[1])
+            # the streamed tiles of a unit are covered exactly once, by at most two CTAs: the piece that starts at tile 0
+            # writes partial 0 (and clears partial 1 when it is the whole unit), the other piece writes partial 1
+            assert len(parts) <= 2 and parts[0][1] == 0 and parts[-1][2] == nt
+            assert all(a[2] == b[1] for a, b in zip(parts, parts[1:]))
+            assert len({p[0] for p in parts}) == len(parts)
+        # batched launches cut every layer where a single-layer launch cuts it: bit-identical partial folds
+        one, _ = _tile_ranges(H, nt, 1, grid, pair)
+        for layer in range(layers):
+            mine = [(c, u - layer * upl, a, b) for c, l, u, a, b in steps if l == layer]
+            assert mine == [(c, u, a, b) for c, _, u, a, b in one]
+        # every CTA gets the same number of tile-steps per layer, +-1
+        per = {}
+        for cta, layer, u, tb0, tb1 in steps:
+            per[(cta, layer)] = per.get((cta, layer), 0) + tb1 - tb0
+        assert max(per.values()) - min(per.values()) <= 1
