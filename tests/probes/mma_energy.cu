@@ -1,6 +1,8 @@
 // GPU probe (standalone): what does a tcgen05.mma stream cost at the board's power cap?
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -o build/mma_energy tests/probes/mma_energy.cu
-//   build/mma_energy <variant> <seconds>      variant: n128 | n256 | n128s | n256s   (s = B operand streamed from L2)
+//   build/mma_energy <variant> <seconds>      variant: n128 | n256 | n128s | n256s (s = B operand streamed from L2) | cg2
+//   cg2 (NOT YET RUN on hardware - written when the round's GPU budget was spent): CTA pairs, tcgen05.mma.cta_group::2 with
+//   M = 256, N = 256, operands resident; every CTA holds its 128 rows of A and its half (128 rows) of B.
 // One CTA per SM; one elected lane issues bf16 128 x N x 16 MMAs (cta_group::1, fp32 accumulators in TMEM) back to back on
 // operands that sit in shared memory (pseudo-random bf16, K-major, 128-byte swizzle layout as in pivot_score.cu).  With
 // "s" a second lane refills the B tile from a 4 MB (L2-resident) global buffer with one bulk copy per 128 x N x 128 tile,
@@ -126,6 +128,119 @@ __global__ void __launch_bounds__(128, 1) mma_loop(long long tiles, const uint8_
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------- cta_group::2
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// one CTA pair = one 256 x 256 x 128 tile-step: the leader issues 8 MMAs (K = 16 each); A: 128 rows per CTA, B: 128 of the
+// 256 rows per CTA, D: 128 lanes x 256 columns in each CTA's TMEM
+__global__ void __launch_bounds__(128, 1) mma_loop_cg2(long long tiles, int* err) {
+    constexpr int N = 256;
+    extern __shared__ __align__(1024) uint8_t raw[];
+    const uint32_t base = (smem_u32(raw) + 1023u) & ~1023u;
+    uint8_t* sm = raw + (base - smem_u32(raw));
+    constexpr uint32_t kA = 128 * 128 * 2, kBh = (N / 2) * 128 * 2, kAtomA = 128 * 64 * 2, kAtomB = (N / 2) * 64 * 2;
+    const uint32_t a0 = base, b0 = base + kA, bars = base + kA + kBh;
+    __shared__ uint32_t tmem_slot;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    for (uint32_t i = threadIdx.x; i < (kA + kBh) / 2; i += blockDim.x) {
+        uint32_t h = (i + blockIdx.x * 7919u) * 2654435761u;
+        h ^= h >> 15;
+        reinterpret_cast<uint16_t*>(sm)[i] = (uint16_t)(0x3f00u | (h & 0x80ffu));
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bars, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();                                                // both CTAs' operands, barriers and TMEM are ready
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = tmem_slot;
+    constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+    if (warp == 0 && lane == 0) {
+        if (rank == 0) {
+            for (long long t = 0; t < tiles; ++t) {
+                const int buf = (int)(t & 1);
+#pragma unroll
+                for (int ks = 0; ks < 8; ++ks) {
+                    const uint32_t offa = (ks >> 2) * kAtomA + (ks & 3) * 32, offb = (ks >> 2) * kAtomB + (ks & 3) * 32;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                                 ::"r"(tmem + buf * N), "l"(desc_sw128(a0 + offa)), "l"(desc_sw128(b0 + offb)), "r"(idesc),
+                                   "r"(ks > 0 ? 1u : 0u) : "memory");
+                }
+            }
+            // completion of everything issued so far, signalled on the barrier at this offset in BOTH CTAs
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(bars), "h"((uint16_t)3) : "memory");
+        }
+        mbar_wait(bars, 0, err);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
+}
+
+static int run_cg2(double seconds, int* err) {
+    constexpr int N = 256;
+    const size_t smem = 128 * 128 * 2 + (size_t)(N / 2) * 128 * 2 + 64 + 1024;
+    CK(cudaFuncSetAttribute(mma_loop_cg2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int sms = 0;
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
+    sms &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sms);
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    const long long tiles = 100000;                                    // 256 x 256 x 128 steps per launch and CTA pair
+    CK(cudaLaunchKernelEx(&cfg, mma_loop_cg2, (long long)1000, err));
+    CK(cudaDeviceSynchronize());
+    double total_ms = 0;
+    long long launches = 0;
+    while (total_ms < seconds * 1e3) {
+        CK(cudaEventRecord(e0));
+        CK(cudaLaunchKernelEx(&cfg, mma_loop_cg2, tiles, err));
+        CK(cudaEventRecord(e1));
+        CK(cudaDeviceSynchronize());
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        total_ms += ms;
+        ++launches;
+        int h = 0;
+        CK(cudaMemcpy(&h, err, sizeof(int), cudaMemcpyDeviceToHost));
+        if (h) { printf("barrier wait timed out - aborting\n"); return 2; }
+    }
+    const double flops = 2.0 * 256 * N * 128 * (double)tiles * (sms / 2) * launches;
+    printf("{\"variant\": \"cg2\", \"ms_total\": %.1f, \"tflops\": %.1f, \"ns_per_256x256x128_step\": %.1f}\n", total_ms,
+           flops / (total_ms * 1e-3) / 1e12, total_ms * 1e6 / ((double)tiles * launches));
+    return 0;
+}
+
 template <int N, bool STREAM>
 static int run(double seconds, const uint8_t* gsrc, size_t gbytes, int* err) {
     const size_t smem = 128 * 128 * 2 + 2 * (size_t)N * 128 * 2 + 64 + 1024;
@@ -174,6 +289,7 @@ int main(int argc, char** argv) {
     if (!strcmp(v, "n256")) return run<256, false>(seconds, g, gbytes, err);
     if (!strcmp(v, "n128s")) return run<128, true>(seconds, g, gbytes, err);
     if (!strcmp(v, "n256s")) return run<256, true>(seconds, g, gbytes, err);
+    if (!strcmp(v, "cg2")) return run_cg2(seconds, err);
     printf("unknown variant %s\n", v);
     return 1;
 }

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/../.."
 S=${1:-3}
 mkdir -p gpurun_out
 : > gpurun_out/mma_energy.txt
-for v in n128 n256 n128s n256s; do
+for v in n128 n256 n128s n256s cg2; do
   nvidia-smi --query-gpu=power.draw,clocks.sm --format=csv,noheader,nounits -lms 100 -i 0 > gpurun_out/mma_energy_$v.smi &
   SMI=$!
   timeout 60 build/mma_energy $v $S >> gpurun_out/mma_energy.txt 2>&1
