@@ -110,9 +110,10 @@ def test_deferred_against_reference_scores():
         data.append((q, k, v))
         entries.append(cache._deferred[-1]["outs"])
     assert len(cache._deferred) == layers
-    n0 = __import__("retake._native", fromlist=["x"]).launch_count()
+    from retake import _native
+    n0 = _native.launch_count()
     cache.after_forward()
-    assert __import__("retake._native", fromlist=["x"]).launch_count() - n0 == 6       # one chain for all layers (no un-rotation)
+    assert _native.launch_count() - n0 == 6                 # one chain of launches for all layers (no un-rotation here)
     keep = int(ratio * L)
     for layer, ((q, k, v), outs) in enumerate(zip(data, entries)):
         ref = ref_head_scores_cuda(q, k)
