@@ -16,6 +16,8 @@
  *     host synchronisation, no global state; the caller owns every buffer including `workspace`;
  *   - return value: 0 = ok; >0 = cudaError_t from a launch; <0 = RTK_E_* argument error
  *     (rtk_error_string() turns either into text);
+ *   - every compute entry point opens an NVTX range named after itself on the calling thread (visible in nsys / ncu
+ *     --nvtx; a no-op without a profiler attached);
  *   - the PivotKV and MA-LLM kernels are launched with programmatic dependent launch (each kernel waits for its
  *     predecessor on the stream with griddepcontrol.wait before touching memory); RTK_NO_PDL=1 in the environment
  *     of the process falls back to plain launches.
@@ -39,6 +41,10 @@ extern "C" {
 #define RTK_E_DRIVER      (-5)  /* could not obtain cuTensorMapEncodeTiled from the driver  */
 
 int         rtk_version(void);
+/* 16 hex digits: SHA-256 over the library's sources (csrc/*.cu, csrc/*.cuh, include/rtk_b200.h; build.py computes it
+ * and compiles it in).  bench.py and smoke() print it, and the Python binding refuses a library whose id does not match
+ * the sources lying next to it, so a record always says which sources ran. */
+const char* rtk_build_id(void);
 const char* rtk_error_string(int code);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t     rtk_launch_count(void);

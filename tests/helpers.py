@@ -36,3 +36,25 @@ def scene_video(g, T, N, C, sigma=0.3, dup_every=0):
         for t in range(dup_every, T, dup_every):
             x[t] = x[t - 1]                               # exact duplicates -> dis == 0 ties
     return x
+
+
+def index_parity(idx, idx_ref, score_ref, keep):
+    """Compare a kept-index set with the reference's ``topk(score, keep).indices.sort()`` (longvideo_cache.py:276-277).
+
+    Returns (identical, justified, n_diff): ``identical`` is exact equality; when the sets differ, ``justified`` says
+    whether EVERY index in the symmetric difference carries a reference score within one bf16 ulp of the reference's
+    k-th largest score - the only place where cuBLAS' accumulation order (which no other kernel can replay, SURVEY.md
+    note N4) may legitimately move a token across the cut.  ``score_ref`` is the reference's bf16 score AFTER the
+    key-patch fill."""
+    idx, idx_ref = idx.long(), idx_ref.long()
+    if idx.numel() == idx_ref.numel() and bool(torch.equal(idx, idx_ref)):
+        return True, True, 0
+    a = torch.zeros(score_ref.numel(), dtype=torch.bool, device=score_ref.device)
+    b = a.clone()
+    a[idx] = True
+    b[idx_ref] = True
+    diff = torch.nonzero(a ^ b)[:, 0]
+    bits = score_ref.to(torch.bfloat16).view(torch.int16).int()          # scores are positive: bit patterns are ordered
+    kth = torch.sort(bits, descending=True).values[keep - 1]
+    ok = bool(((bits[diff] - kth).abs() <= 1).all()) and idx.numel() == idx_ref.numel() == keep
+    return False, ok, int(diff.numel())

@@ -1,8 +1,8 @@
 #!/bin/bash
-# Build library variants for the A/B probes: tests/probes/build_ab.sh name "-DFLAG=1 ..." [name2 "..."] ...
+# Build library variants for the A/B probes: tests/probes/lab/build_ab.sh name "-DFLAG=1 ..." [name2 "..."] ...
 # -> build/ab/librtk_<name>.so (git-ignored, travels to the GPU box)
 set -e
-cd "$(dirname "$0")/../.."
+cd "$(dirname "$0")/../../.."
 SRC=video-retake_b200/csrc
 mkdir -p build/ab
 while [ $# -gt 0 ]; do

@@ -16,38 +16,56 @@
 //
 // Warp roles (576 threads): warp 0 TMA producer, warp 1 TMEM allocator + MMA issuer (one elected lane), warps 2-17
 // four softmax groups of four warps (one warp per TMEM lane quarter): groups 0, 1 serve the accumulators of the first
-// stationary tile, groups 2, 3 those of the second, each taking 64 of the 128 columns with one tcgen05.ld.32x32b.x64.
-// Per logit the softmax side issues two in-place fp32->bf16 roundings (F2FP with a zero low half), packed f32x2
-// scale / FMA / add, one exp2 and (pass 1) half an FMNMX3.  exp2 is MUFU.EX2, except for RTK_SCORE_POLY_P1 / _P2 of
-// every 16 logit pairs, which take a degree-5 polynomial on the FMA pipe (same accuracy class, see ex2_poly2): the
-// MUFU pipe (16 results per clock and SM) is the busiest unit of the kernel.
-// This file holds the shipped configuration only; the A/B variants of round 1 (ring depths, 16/32-column TMEM loads,
-// more softmax groups, lazy rescale ...) live in tests/probes/lab/pivot_score_r1_variants.cu with their results in
-// profiles/r1_score_ab_experiments.md.
+// stationary tile, groups 2, 3 those of the second, each taking 64 of the 128 columns with one tcgen05.ld.32x32b.x64
+// (-DRTK_SCORE_PAIR=0: one stationary tile per unit, 4-stage ring, accumulator tile n -> groups 2(n&1), 2(n&1)+1).  Per logit the softmax side issues two
+// in-place fp32->bf16 roundings (F2FP with a zero low half), packed f32x2 scale / FMA / add, one MUFU.EX2 and (pass 1)
+// half an FMNMX3; what bounds it is the MUFU pipe and the softmax warps' issue slots (profiles/r1_score_ab_experiments.md).
+// Every -DRTK_SCORE_* flag below is an A/B switch documented there; the defaults are the shipped configuration.
 #include <cuda.h>
 
 #include "rtk_common.cuh"
+
+#ifndef RTK_SCORE_EXPERIMENT_NOMATH
+#define RTK_SCORE_EXPERIMENT_NOMATH 0
+#endif
+#ifndef RTK_SCORE_EXPERIMENT_NOLOAD
+#define RTK_SCORE_EXPERIMENT_NOLOAD 0
+#endif
+#ifndef RTK_SCORE_EXPERIMENT_NOEXP
+#define RTK_SCORE_EXPERIMENT_NOEXP 0
+#endif
 
 namespace rtk {
 
 constexpr int kTile = 128;            // rows of both operand tiles, = UMMA M = UMMA N
 constexpr int kHeadDim = 128;         // largest D: two 64-element swizzle atoms (D = 64 uses one)
-constexpr int kPair = 2;              // stationary tiles per unit: every streamed tile feeds two MMAs
-constexpr int kStages = 2;            // streamed-operand ring depth (a stage lasts two MMAs)
-constexpr int kASlots = 2;            // stationary-pair slots: the next unit's pair is fetched while this unit computes
+#ifndef RTK_SCORE_PAIR
+#define RTK_SCORE_PAIR 1              // 1 (default): a unit keeps TWO stationary tiles and every streamed tile feeds two MMAs - half
+#endif                                //    the L2 -> shared-memory traffic per flop (profiles/r1_mma_energy_probe.txt: ~35-40 pJ per
+                                      //    byte).  Same box, sustained: 0.3363 -> 0.3207 ms per layer, 3070 -> 3202 frames/s.  0: one tile.
+#ifndef RTK_SCORE_STAGES
+#define RTK_SCORE_STAGES (RTK_SCORE_PAIR ? 2 : 4)   // streamed-operand ring depth (a paired stage lasts two MMAs)
+#endif
+constexpr int kPair = RTK_SCORE_PAIR ? 2 : 1;   // stationary tiles per unit
+constexpr int kStages = RTK_SCORE_STAGES;
+#ifndef RTK_SCORE_ASLOTS
+#define RTK_SCORE_ASLOTS 2            // stationary-tile slots: 2 = the next unit's tile is fetched while this unit still computes
+#endif
+constexpr int kASlots = RTK_SCORE_ASLOTS;
 constexpr int kAccBufs = 4;           // 128-column TMEM buffers
+#ifndef RTK_SCORE_EARLY_RELEASE
+#define RTK_SCORE_EARLY_RELEASE 0     // 1: hand the accumulator buffer back as soon as it sits in registers (A/B: no gain)
+#endif
 // pass 2: per-tile c_q rows.  A slot is rewritten for tile c after MMA(c - kStages) was issued, i.e. after tile
-// c - kStages - kAccBufs was released (= fully processed) by the softmax side.
-constexpr int kStatSlots = kStages + kAccBufs;
+// c - kStages - kAccBufs was released by the softmax side.  Released = processed without early release; with it a warp
+// has only finished the tile BEFORE the one it released (c - kStages - kAccBufs - 2 of the same group pair, one more
+// for the other pair), hence four more slots.
+#ifndef RTK_SCORE_PIPE2
+#define RTK_SCORE_PIPE2 0             // pass 2: 32-column TMEM loads software-pipelined across tiles (releases buffers early too)
+#endif
+constexpr int kStatSlots = kStages + kAccBufs + ((RTK_SCORE_EARLY_RELEASE || RTK_SCORE_PIPE2) ? 4 : 0);
 constexpr uint32_t kTileBytes = kTile * kHeadDim * 2;        // 32 KiB
 constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] swizzle-128B box
-
-#ifndef RTK_SCORE_POLY_P1
-#define RTK_SCORE_POLY_P1 0           // pass 1: logit pairs out of every 16 whose exp2 runs on the FMA pipe
-#endif
-#ifndef RTK_SCORE_POLY_P2
-#define RTK_SCORE_POLY_P2 0           // pass 2: the same
-#endif
 
 struct ScoreSmem {
     // offsets inside dynamic shared memory (1024-byte aligned base)
@@ -55,9 +73,9 @@ struct ScoreSmem {
     static constexpr uint32_t b_ring = kASlots * kPair * kTileBytes;
     static constexpr uint32_t stats = b_ring + kStages * kTileBytes;                 // [kStatSlots][128] f32
     static constexpr uint32_t merge = stats + kStatSlots * kTile * 4;                // [4][128][2] f32
-    static constexpr uint32_t bars = merge + 4 * kTile * 2 * 4;
-    // barriers: a_full[2], a_empty[2], b_full[kStages], b_empty[kStages], t_full[4], t_empty[4], st_full[kStatSlots]
-    static constexpr uint32_t n_bars = 4 + 2 * kStages + 2 * kAccBufs + kStatSlots;
+    static constexpr uint32_t bars = merge + 8 * kTile * 2 * 4;          // up to 8 groups
+    // barriers: a_full[2], a_empty[2], b_full[4], b_empty[4], t_full[4], t_empty[4], st_full[8], port
+    static constexpr uint32_t n_bars = 4 + 2 * kStages + 2 * kAccBufs + kStatSlots + 1;
     static constexpr uint32_t tmem_ptr = bars + n_bars * 8;
     static constexpr uint32_t total = tmem_ptr + 16;
 };
@@ -83,7 +101,28 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
@@ -102,6 +141,14 @@ __device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&r)[64]) {
         : "r"(taddr)
         : "memory");
 }
+// wait for the outstanding TMEM loads; the registers are listed so that no use of them can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 // acc(fp32) += one half of a packed bf16x2 (SASS FHADD.BF16, no unpack needed)
 __device__ __forceinline__ void add_bf16_pair(float& acc_lo, float& acc_hi, uint32_t packed) {
     asm("{\n\t.reg .b16 lo, hi;\n\t"
@@ -119,9 +166,13 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         : "memory");
 }
 __device__ __forceinline__ float ex2f(float x) {
+#if RTK_SCORE_EXPERIMENT_NOEXP             // timing experiment: everything but the MUFU
+    return x * 0.5f;
+#else
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
+#endif
 }
 __device__ __forceinline__ float lg2f(float x) {
     float y;
@@ -138,7 +189,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTile >> 3) << 17) | ((uint32_t)(kTile >> 4) << 24);
 
 // Several layers of one chunk can be scored by the same pair of launches (rtk_pivot_update_batch): the unit space is
-// (layer, head, stationary tile pair) and every layer brings its own pair of tensor maps.
+// (layer, head, stationary tile) and every layer brings its own pair of tensor maps.
 template <int NL>
 struct ScoreMaps {
     CUtensorMap q[NL], k[NL];
@@ -181,15 +232,24 @@ __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// bf16x2 -> (lo, hi) widened to fp32, packed for the x2 pipes
+__device__ __forceinline__ uint64_t widen2(uint32_t p) { return pk2(bf16lo_to_f32(p), bf16hi_to_f32(p)); }
 
-// wait used by the producer and MMA-issuer warps
+#ifndef RTK_SCORE_FEEDER_SLEEP
+#define RTK_SCORE_FEEDER_SLEEP 0     // ns the TMA / MMA warps sleep between mbarrier polls (0: spin)
+#endif
+// wait used by the producer and MMA-issuer warps: they share their scheduler with four softmax warps, and a tight poll
+// loop takes issue slots away from them
 __device__ __forceinline__ void mbar_wait_feeder(uint32_t bar, uint32_t parity) {
     while (!mbar_try_wait(bar, parity)) {
+        if (RTK_SCORE_FEEDER_SLEEP > 0) __nanosleep(RTK_SCORE_FEEDER_SLEEP);
     }
 }
 
-// fp32 -> nearest bf16, returned as fp32: one F2FP.BF16.F32.PACK_AB whose low half is RZ - the packed result with a
-// zero low half IS the rounded fp32 value, so no widening instruction follows
+#ifndef RTK_SCORE_RZPACK
+#define RTK_SCORE_RZPACK 1     // round to bf16 in place (F2FP with a zero low half: the result IS the fp32 value; default, -5 %) vs pack + widen (0)
+#endif
+// fp32 -> nearest bf16, returned as fp32: one F2FP.BF16.F32.PACK_AB whose low half is RZ
 __device__ __forceinline__ float round_bf16_inplace(float a) {
     uint32_t d;
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(a), "f"(0.f));
@@ -198,93 +258,139 @@ __device__ __forceinline__ float round_bf16_inplace(float a) {
 
 // the reference's logit rounding chain on a pair of raw accumulators: bf16(acc) then bf16(x * inv_sqrt_d); fp32 out
 __device__ __forceinline__ uint64_t logit_chain2(uint32_t r0, uint32_t r1, uint64_t inv2) {
+#if RTK_SCORE_RZPACK
     float t0, t1;
     upk2(mul2(pk2(round_bf16_inplace(__uint_as_float(r0)), round_bf16_inplace(__uint_as_float(r1))), inv2), t0, t1);
     return pk2(round_bf16_inplace(t0), round_bf16_inplace(t1));
+#endif
+    const uint32_t p1 = pack_bf16x2_rn(__uint_as_float(r0), __uint_as_float(r1));
+    float s0, s1;
+    upk2(mul2(widen2(p1), inv2), s0, s1);
+    return widen2(pack_bf16x2_rn(s0, s1));
 }
 __device__ __forceinline__ float logit_chain1(float acc, float inv) { return round_bf16(round_bf16(acc) * inv); }
 
-// exp2 of a packed pair: two MUFU.EX2 ...
-__device__ __forceinline__ uint64_t ex2_mufu2(uint64_t x2) {
-    float x0, x1;
-    upk2(x2, x0, x1);
-    return pk2(ex2f(x0), ex2f(x1));
-}
-// ... or, to take load off the MUFU pipe, on the FMA pipe: x = n + f with n = rint(x), f in [-0.5, 0.5]; 2^f by a
-// degree-5 minimax polynomial (relative error 2.3e-7 evaluated in fp32 = 2^-22.1, the class of ex2.approx: 2^-22.5),
-// 2^n spliced into the exponent field.  Inputs below -125 (masked columns: -inf) give 2^-125 instead of 0, which no
-// fp32 sum next to a term >= 2^-24 can see.
-__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x2) {
-    float x0, x1;
-    upk2(x2, x0, x1);
-    x2 = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
-    const float magic = 12582912.f;                              // 1.5 * 2^23: t = magic + rint(x) exactly
-    const uint64_t t2 = add2(x2, pk2(magic, magic));
-    const uint64_t f2 = add2(x2, fma2(t2, pk2(-1.f, -1.f), pk2(magic, magic)));      // x - (t - magic)
-    uint64_t p2 = pk2(0.0013280266430228949f, 0.0013280266430228949f);
-    p2 = fma2(p2, f2, pk2(0.009676850400865078f, 0.009676850400865078f));
-    p2 = fma2(p2, f2, pk2(0.055507123470306396f, 0.055507123470306396f));
-    p2 = fma2(p2, f2, pk2(0.24022091925144196f, 0.24022091925144196f));
-    p2 = fma2(p2, f2, pk2(0.6931469440460205f, 0.6931469440460205f));
-    p2 = fma2(p2, f2, pk2(1.0000001192092896f, 1.0000001192092896f));
-    float t0, t1, p0, p1;
-    upk2(t2, t0, t1);
-    upk2(p2, p0, p1);
-    // magic's bit pattern ends in 22 zeros, so (bits(t) << 23) = rint(x) * 2^23 (mod 2^32): add it to the exponent field
-    return pk2(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23)),
-               __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
-}
-// pair j of a 64-column block (j = 0..31): which unit evaluates its exp2
-template <int POLY>
-__device__ __forceinline__ uint64_t ex2_pair(uint64_t x2, int j) {
-    // spread the polynomial pairs evenly over each group of 16: pair j takes it when floor(j*POLY/16) steps up
-    if (POLY > 0 && ((j % 16) * POLY) / 16 != (((j % 16) + 1) * POLY) / 16) return ex2_poly2(x2);
-    return ex2_mufu2(x2);
-}
+#ifndef RTK_SCORE_X16
+#define RTK_SCORE_X16 0        // 16-column TMEM loads, double buffered (1) vs 32-column blocking loads (0)
+#endif
+#ifndef RTK_SCORE_X64
+#define RTK_SCORE_X64 1          // one 64-column TMEM load per tile half (default; -2 % vs two 32-column loads)
+#endif
+#ifndef RTK_SCORE_PORT
+#define RTK_SCORE_PORT 0
+#endif
+#ifndef RTK_SCORE_X32DB
+#define RTK_SCORE_X32DB 0
+#endif
+#ifndef RTK_SCORE_FHADD
+#define RTK_SCORE_FHADD 1      // pass 2: accumulate bf16 halves with FHADD.BF16 (1, default) vs widen + packed fp32 add (0)
+#endif
+#ifndef RTK_SCORE_LAZY
+#define RTK_SCORE_LAZY 0       // pass 1: rescale only when some lane's maximum grew (1) vs every step (0)
+#endif
+#ifndef RTK_SCORE_TREEMAX
+#define RTK_SCORE_TREEMAX 0
+#endif
+#ifndef RTK_SCORE_EXPERIMENT_EX2_BF16X2
+#define RTK_SCORE_EXPERIMENT_EX2_BF16X2 0
+#endif
+#ifndef RTK_SCORE_CHAINS
+#define RTK_SCORE_CHAINS 1     // independent accumulation chains
+#endif
 
 struct SoftmaxState {
     float m = -INFINITY;                                     // pass 1: running max (scaled-logit domain)
-    uint64_t acc = 0;                                        // pass 1: packed fp32x2 row sum
-    float c0 = 0.f, c1 = 0.f;                                // pass 2: column sums
+    uint64_t acc = 0, acc_b = 0;                             // packed fp32x2 sums (pass 1 row sum / pass 2 column sum)
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;            // pass 2 column sums when FHADD is used
 };
 
-// 64 consecutive accumulator columns of one TMEM lane (one row of the stationary tile)
-template <int PASS>
-__device__ __forceinline__ void softmax_cols(uint32_t (&r)[64], int valid, SoftmaxState& st, const float* cq, float inv,
-                                             uint64_t inv2, uint64_t l2e2) {
-    constexpr int NC = 64;
+// NC consecutive accumulator columns of one TMEM lane (one row of the stationary tile)
+template <int PASS, int NC>
+__device__ __forceinline__ void softmax_cols(uint32_t (&r)[NC], int col0, int valid, SoftmaxState& st, const float* cq,
+                                             float inv, uint64_t inv2, uint64_t l2e2) {
+#if RTK_SCORE_EXPERIMENT_NOMATH            // timing experiment: MMA + TMEM load pipeline only
+    {
+        float mx = __uint_as_float(r[0]);
+#pragma unroll
+        for (int i = 1; i < NC; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        st.m = fmaxf(st.m, mx);
+        return;
+    }
+#endif
     if (PASS == 1) {
-        if (valid < NC) {
+        if (valid < 64) {
 #pragma unroll
             for (int i = 0; i < NC; ++i)
-                if (i >= valid) r[i] = 0xff800000u;          // -inf: padded key column
+                if (col0 + i >= valid) r[i] = 0xff800000u;   // -inf: padded key column
         }
         // the rounding chain is monotone, so the row max of the rounded logits is the chain of the raw max
+#if RTK_SCORE_TREEMAX
+        float m4[NC / 4];
+#pragma unroll
+        for (int i = 0; i < NC / 4; ++i)
+            m4[i] = fmaxf(fmaxf(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1])),
+                          fmaxf(__uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3])));
+        float mx = m4[0];
+#pragma unroll
+        for (int i = 1; i < NC / 4; ++i) mx = fmaxf(mx, m4[i]);
+#else
         float mx = fmaxf(fmaxf(__uint_as_float(r[0]), __uint_as_float(r[1])), __uint_as_float(r[2]));
 #pragma unroll
         for (int i = 3; i < NC - 1; i += 2) mx = fmaxf(fmaxf(mx, __uint_as_float(r[i])), __uint_as_float(r[i + 1]));
         mx = fmaxf(mx, __uint_as_float(r[NC - 1]));
+#endif
         const float mn = fmaxf(st.m, logit_chain1(mx, inv));
+#if RTK_SCORE_LAZY
+        if (__any_sync(0xffffffffu, mn > st.m)) {            // rare after the first few steps
+            const float sc = (mn > -INFINITY) ? ex2f((st.m - mn) * kLog2e) : 0.f;
+            st.acc = mul2(st.acc, pk2(sc, sc));
+            st.acc_b = mul2(st.acc_b, pk2(sc, sc));
+            st.m = mn;
+        }
+        const float mm = (st.m > -INFINITY) ? st.m * kLog2e : 0.f;
+#else
         if (!(mn > -INFINITY)) return;
         const float mm = mn * kLog2e;
         const float sc = ex2f(fmaf(st.m, kLog2e, -mm));      // m == -inf -> 0
         st.acc = mul2(st.acc, pk2(sc, sc));
+        if (RTK_SCORE_CHAINS > 1) st.acc_b = mul2(st.acc_b, pk2(sc, sc));
         st.m = mn;
+#endif
         const uint64_t nmm = pk2(-mm, -mm);
 #pragma unroll
         for (int i = 0; i < NC; i += 4) {
-            st.acc = add2(st.acc, ex2_pair<RTK_SCORE_POLY_P1>(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), i / 2));
-            st.acc = add2(st.acc, ex2_pair<RTK_SCORE_POLY_P1>(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, nmm), i / 2 + 1));
+            float y0, y1, y2, y3;
+            upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), y0, y1);
+            upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, nmm), y2, y3);
+#if RTK_SCORE_EXPERIMENT_EX2_BF16X2       // throughput experiment only (8-bit exps are not accurate enough)
+            uint32_t e01 = pack_bf16x2_rn(y0, y1), e23 = pack_bf16x2_rn(y2, y3);
+            asm("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(e01));
+            asm("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(e23));
+            st.acc = add2(st.acc, widen2(e01));
+            st.acc = add2(st.acc, widen2(e23));
+#else
+            st.acc = add2(st.acc, pk2(ex2f(y0), ex2f(y1)));
+            if (RTK_SCORE_CHAINS > 1) st.acc_b = add2(st.acc_b, pk2(ex2f(y2), ex2f(y3)));
+            else st.acc = add2(st.acc, pk2(ex2f(y2), ex2f(y3)));
+#endif
         }
     } else {
 #pragma unroll
         for (int i = 0; i < NC; i += 4) {
-            const float4 cc = *reinterpret_cast<const float4*>(cq + i);
-            float e0, e1, e2, e3;
-            upk2(ex2_pair<RTK_SCORE_POLY_P2>(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y)), i / 2), e0, e1);
-            upk2(ex2_pair<RTK_SCORE_POLY_P2>(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w)), i / 2 + 1), e2, e3);
-            add_bf16_pair(st.c0, st.c1, pack_bf16x2_rn(e0, e1));
-            add_bf16_pair(st.c0, st.c1, pack_bf16x2_rn(e2, e3));
+            const float4 cc = *reinterpret_cast<const float4*>(cq + col0 + i);
+            float y0, y1, y2, y3;
+            upk2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y)), y0, y1);
+            upk2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w)), y2, y3);
+            const uint32_t p01 = pack_bf16x2_rn(ex2f(y0), ex2f(y1)), p23 = pack_bf16x2_rn(ex2f(y2), ex2f(y3));
+#if RTK_SCORE_FHADD
+            add_bf16_pair(st.c0, st.c1, p01);
+            if (RTK_SCORE_CHAINS > 1) add_bf16_pair(st.c2, st.c3, p23);
+            else add_bf16_pair(st.c0, st.c1, p23);
+#else
+            st.acc = add2(st.acc, widen2(p01));
+            if (RTK_SCORE_CHAINS > 1) st.acc_b = add2(st.acc_b, widen2(p23));
+            else st.acc = add2(st.acc, widen2(p23));
+#endif
         }
     }
 }
@@ -293,12 +399,23 @@ __device__ __forceinline__ void softmax_cols(uint32_t (&r)[64], int valid, Softm
 // number of tile-steps (+-1) and a unit is shared by at most two CTAs (range length >= nt).  With several layers in the
 // launch the CTA takes ITS range of every layer in turn - the cut points inside a layer are those of a single-layer
 // launch, so batched and per-layer scoring fold their fp32 partials in the same order and agree bit for bit.
+#ifndef RTK_SCORE_EVEN_RANGES
+#define RTK_SCORE_EVEN_RANGES 0     // 1: even-aligned tile ranges (A/B: no gain)
+#endif
 struct TileRange {
     long long g, g1, Gl;
     int nt, layer, n_layers, units_per_layer;
     __device__ __forceinline__ void set_layer_range() {
         g = Gl * blockIdx.x / gridDim.x;
         g1 = Gl * (blockIdx.x + 1) / gridDim.x;
+#if RTK_SCORE_EVEN_RANGES
+        // consecutive tiles alternate between the two softmax group pairs: with an even number of tiles per unit every
+        // (partial) unit of an even-aligned range gives both pairs the same amount of work before they meet at the merge
+        if ((nt & 1) == 0) {
+            g = 2 * ((Gl / 2) * blockIdx.x / gridDim.x);
+            g1 = 2 * ((Gl / 2) * (blockIdx.x + 1) / gridDim.x);
+        }
+#endif
     }
     // H: heads of all layers, Hl: heads per layer; a head has ceil(nt / kPair) units of kPair stationary tiles
     __device__ __forceinline__ TileRange(int H, int Hl, int nt_) : nt(nt_), layer(0) {
@@ -307,7 +424,7 @@ struct TileRange {
         Gl = (long long)units_per_layer * nt_;
         set_layer_range();
     }
-    // u: unit index over all layers (= head-of-all-layers * units per head + stationary tile pair)
+    // u: unit index over all layers (= head-of-all-layers * units per head + stationary tile (pair))
     __device__ __forceinline__ bool next(int& u, int& tb0, int& tb1) {
         while (g >= g1) {
             if (++layer >= n_layers) return false;
@@ -323,10 +440,17 @@ struct TileRange {
     }
 };
 
-constexpr int kGroups = 4;                          // softmax groups of four warps (one warp per TMEM lane quarter)
-constexpr int kSoftmaxWarps = 4 * kGroups;
+#ifndef RTK_SCORE_GROUPS
+#define RTK_SCORE_GROUPS 0     // 0: four groups, tiles alternate between two group pairs (64 columns per group);
+#endif                         // G > 0: G groups take the 32-column chunks of all tiles round robin
+constexpr int kGroups = RTK_SCORE_GROUPS ? RTK_SCORE_GROUPS : 4;
+constexpr int kSoftmaxWarps = 4 * kGroups;     // groups of four warps (one per TMEM lane quarter)
 constexpr int kScoreThreads2 = (2 + kSoftmaxWarps) * 32;
-constexpr int kTileArrivals = 8;                    // softmax-warp arrivals that free one accumulator buffer (two groups)
+#ifndef RTK_SCORE_GCOLS
+#define RTK_SCORE_GCOLS 32     // chunk width of the round-robin scheme
+#endif
+constexpr int kChunksPerTile = 128 / RTK_SCORE_GCOLS;
+constexpr int kTileArrivals = RTK_SCORE_GROUPS ? 4 * kChunksPerTile : 8;       // softmax-warp arrivals that free one accumulator buffer
 
 template <int PASS, int NL>
 __global__ void __launch_bounds__(kScoreThreads2, 1)
@@ -346,12 +470,14 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
     auto t_full = [&](int b) { return bar0 + 32 + 8 * (2 * kStages + b); };
     auto t_empty = [&](int b) { return bar0 + 32 + 8 * (2 * kStages + kAccBufs + b); };
     auto st_full = [&](int i) { return bar0 + 32 + 8 * (2 * kStages + 2 * kAccBufs + i); };
+    const uint32_t port = bar0 + 32 + 8 * (2 * kStages + 2 * kAccBufs + kStatSlots);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < 2; ++i) { mbar_init(a_full(i), 1); mbar_init(a_empty(i), 1); }
         for (int s = 0; s < kStages; ++s) { mbar_init(b_full(s), 1); mbar_init(b_empty(s), 1); }
         for (int b = 0; b < kAccBufs; ++b) { mbar_init(t_full(b), 1); mbar_init(t_empty(b), kTileArrivals); }
         for (int i = 0; i < kStatSlots; ++i) mbar_init(st_full(i), 1);
+        mbar_init(port, 8);
         fence_mbar_init();
     }
     if (warp == 1) tmem_alloc(base + ScoreSmem::tmem_ptr, 512);
@@ -370,13 +496,13 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
     const int b_l1 = (PASS == 1) ? prm.k_dim1_is_l : prm.q_dim1_is_l;
     TileRange range(prm.H, prm.Hl, nt);
     int u, tb0, tb1;
-    const int nta = (nt + kPair - 1) / kPair;                // units per head
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             uint32_t cnt = 0, ucnt = 0;
             while (range.next(u, tb0, tb1)) {
+                const int nta = (nt + kPair - 1) / kPair;            // units per head
                 const int hh = u / nta, ta = (u - hh * nta) * kPair; // hh: head index over all layers of the launch; first stationary tile
                 const int layer = (NL == 1) ? 0 : hh / prm.Hl;
                 const int h = hh - layer * prm.Hl;
@@ -384,8 +510,8 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                 const CUtensorMap* b_map = b_maps + layer;
                 const int a_head = (PASS == 1) ? h : h / prm.G;
                 const int b_head = (PASS == 1) ? h / prm.G : h;
-                // stationary pair of this unit into slot ucnt % kASlots: it is on its way while the MMAs of the
-                // previous unit are still running (no pipeline bubble at unit boundaries)
+                // stationary tile of this unit into slot ucnt % kASlots: with two slots it is on its way while the
+                // MMAs of the previous unit are still running (no pipeline bubble at unit boundaries)
                 const int as = ucnt % kASlots;
                 mbar_wait_feeder(a_empty(as), ((ucnt / kASlots) & 1u) ^ 1u);
                 mbar_arrive_expect_tx(a_full(as), kPair * prm.n_atoms * kHalfBytes);
@@ -409,8 +535,8 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                                     b_full(s));
                     }
                     if (PASS == 2) {
-                        // c_q of the 128 streamed queries; slot cnt % kStatSlots was last read for tile cnt - kStatSlots,
-                        // which the softmax side finished before MMA(cnt - kStages) could start, i.e. before b_empty(s) fired
+                        // c_q of the 128 streamed queries; slot cnt % 8 was last read for tile cnt - 8, which the
+                        // softmax side finished before MMA(cnt - 4) could start, i.e. before b_empty(s) fired
                         const int sl = cnt % kStatSlots;
                         mbar_arrive_expect_tx(st_full(sl), kTile * 4u);
                         bulk_g2s(base + ScoreSmem::stats + sl * kTile * 4u,
@@ -426,6 +552,7 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
             const int as = ucnt % kASlots;
             mbar_wait_feeder(a_full(as), (ucnt / kASlots) & 1u);
             ++ucnt;
+#if RTK_SCORE_PAIR
             // streamed tile cnt feeds both stationary tiles: accumulators 2*(cnt&1) (tile 0) and 2*(cnt&1)+1 (tile 1)
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 const int s = cnt % kStages, bp = 2 * (int)(cnt & 1u);
@@ -452,10 +579,31 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                 }
                 __syncwarp();
             }
+#else
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                const int s = cnt % kStages, b = cnt % kAccBufs;
+                mbar_wait_feeder(b_full(s), (cnt / kStages) & 1u);
+                mbar_wait_feeder(t_empty(b), ((cnt / kAccBufs) & 1u) ^ 1u);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint32_t a0 = base + ScoreSmem::a_tile + as * kTileBytes, b0 = base + ScoreSmem::b_ring + s * kTileBytes;
+                    const int nks = prm.n_atoms * 4;
+#pragma unroll 8
+                    for (int ks = 0; ks < nks; ++ks) {
+                        const uint32_t off = (ks >> 2) * kHalfBytes + (ks & 3) * 32;
+                        umma_bf16(tmem_base + b * kTile, umma_desc_sw128(a0 + off), umma_desc_sw128(b0 + off), kIdesc,
+                                  ks > 0 ? 1u : 0u);
+                    }
+                    tc_commit(b_empty(s));
+                    tc_commit(t_full(b));
+                    if (tb == tb1 - 1) tc_commit(a_empty(as));
+                }
+                __syncwarp();
+            }
+#endif
         }
     } else {
-        // ====== softmax: 4 groups x 4 warps; groups 0, 1 serve the unit's first stationary tile, groups 2, 3 its second
-        //        one, each taking one 64-column half of every accumulator
+        // ================================== softmax: 4 groups x 4 warps; tile n -> groups 2*(n&1), 2*(n&1)+1 (column halves)
         const int sw = warp - 2;                 // 0..15
         const int grp = sw >> 2;                 // 0..3
         const int quarter = warp & 3;            // TMEM lane quarter this warp may touch
@@ -467,9 +615,17 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
         const uint64_t inv2 = pk2(inv, inv), l2e2 = pk2(kLog2e, kLog2e);
         uint32_t cnt = 0;
         while (range.next(u, tb0, tb1)) {
+#if RTK_SCORE_PAIR
+            // groups 0, 1 serve the unit's first stationary tile, groups 2, 3 its second one (64-column halves each)
+            const int nta = (nt + 1) / 2;
             const int h = u / nta, ta = (u - h * nta) * 2 + (grp >> 1);
             const bool has_tile = ta < nt;           // odd tile count: the last unit's second tile is a repeat, dropped below
+#else
+            const int h = u / nt, ta = u - h * nt;
+            const bool has_tile = true;
+#endif
             SoftmaxState st;
+#if RTK_SCORE_PAIR
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 const int b = 2 * (int)(cnt & 1u) + (grp >> 1);
                 mbar_wait(t_full(b), (cnt >> 1) & 1u);
@@ -481,21 +637,182 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                     uint32_t r[64];
                     tmem_ld64(lane_addr + b * kTile, r);
                     tmem_ld_wait();
-                    softmax_cols<PASS>(r, valid, st, cq, inv, inv2, l2e2);
+                    softmax_cols<PASS, 64>(r, 0, valid, st, cq, inv, inv2, l2e2);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(t_empty(b));
             }
+#elif RTK_SCORE_GROUPS
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                const int b = cnt % kAccBufs;
+                bool waited = false;
+#pragma unroll
+                for (int c = 0; c < kChunksPerTile; ++c) {
+                    if ((int)((cnt * (unsigned)kChunksPerTile + c) % kGroups) != grp) continue;
+                    if (!waited) {
+                        mbar_wait(t_full(b), (cnt / kAccBufs) & 1u);
+                        tc_fence_after();
+                        if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
+                        waited = true;
+                    }
+                    const int valid_c = prm.L - tb * kTile - c * RTK_SCORE_GCOLS;
+                    const float* cqc = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + c * RTK_SCORE_GCOLS;
+                    uint32_t r[RTK_SCORE_GCOLS];
+#if RTK_SCORE_GCOLS == 64
+                    tmem_ld64(tmem_base + ((uint32_t)(quarter * 32) << 16) + b * kTile + c * 64, r);
+#else
+                    tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + b * kTile + c * 32, r);
+#endif
+                    tmem_ld_wait();
+                    softmax_cols<PASS, RTK_SCORE_GCOLS>(r, 0, valid_c, st, cqc, inv, inv2, l2e2);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty(b));
+                }
+            }
+#elif RTK_SCORE_PIPE2
+            if (PASS == 2) {
+                // this warp's tiles of the unit: every other one; its 64 columns of a tile arrive as two 32-column loads,
+                // and the load of the NEXT 32 columns (same tile or the pair's next tile) is in flight during the math
+                uint32_t ra[32], rb[32];
+                uint32_t c = cnt + (((cnt & 1u) != (uint32_t)(grp >> 1)) ? 1u : 0u);       // first owned tile counter
+                int tb = tb0 + (int)(c - cnt);
+                auto ready = [&](uint32_t cc) {
+                    mbar_wait(t_full(cc % kAccBufs), (cc / kAccBufs) & 1u);
+                    tc_fence_after();
+                    mbar_wait(st_full(cc % kStatSlots), (cc / kStatSlots) & 1u);
+                };
+                bool have = tb < tb1;
+                if (have) {
+                    ready(c);
+                    tmem_ld32(lane_addr + (c % kAccBufs) * kTile, ra);
+                    tmem_ld_wait();
+                }
+                while (have) {
+                    const int b = c % kAccBufs;
+                    const int valid = prm.L - tb * kTile - half * 64;
+                    const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (c % kStatSlots) * kTile + half * 64;
+                    tmem_ld32(lane_addr + b * kTile + 32, rb);
+                    softmax_cols<PASS, 32>(ra, 0, valid, st, cq, inv, inv2, l2e2);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty(b));            // both halves sit in registers
+                    const bool more = tb + 2 < tb1;
+                    if (more) {
+                        ready(c + 2);
+                        tmem_ld32(lane_addr + ((c + 2) % kAccBufs) * kTile, ra);
+                    }
+                    softmax_cols<PASS, 32>(rb, 32, valid, st, cq, inv, inv2, l2e2);
+                    if (more) tmem_ld_wait();
+                    c += 2;
+                    tb += 2;
+                    have = more;
+                }
+                cnt += (uint32_t)(tb1 - tb0);
+            } else
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                if ((int)(cnt & 1u) != (grp >> 1)) continue;
+                const int b = cnt % kAccBufs;
+                mbar_wait(t_full(b), (cnt / kAccBufs) & 1u);
+                tc_fence_after();
+                const int valid = prm.L - tb * kTile - half * 64;
+                const float* cq = nullptr;
+                const uint32_t taddr = lane_addr + b * kTile;
+                {
+                    uint32_t r[64];
+                    tmem_ld64(taddr, r);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 64>(r, 0, valid, st, cq, inv, inv2, l2e2);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty(b));
+            }
+#else
+            for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
+                if ((int)(cnt & 1u) != (grp >> 1)) continue;
+                const int b = cnt % kAccBufs;
+                mbar_wait(t_full(b), (cnt / kAccBufs) & 1u);
+                tc_fence_after();
+                if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
+                const int valid = prm.L - tb * kTile - half * 64;      // streamed rows of this half that exist
+                const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + half * 64;
+                const uint32_t taddr = lane_addr + b * kTile;
+#if RTK_SCORE_X16
+                // 64 columns in four 16-column steps; the TMEM load of step j+1 is in flight while step j is computed
+                uint32_t ra[16], rb[16];
+                tmem_ld16(taddr, ra);
+                tmem_ld_wait16(ra);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t (&r)[16] = (j & 1) ? rb : ra;
+                    uint32_t (&rn)[16] = (j & 1) ? ra : rb;
+                    if (j < 3) tmem_ld16(taddr + (j + 1) * 16, rn);
+                    softmax_cols<PASS, 16>(r, j * 16, valid, st, cq, inv, inv2, l2e2);
+                    if (j < 3) tmem_ld_wait16(rn);
+                }
+#elif RTK_SCORE_X64
+                {
+                    uint32_t r[64];
+#if RTK_SCORE_PORT
+                    // TMEM read port token: the eight warps of tile n read their 64 KiB only after those of tile n-1 have
+                    // theirs, so one group pair computes while the other one loads instead of both contending for the port
+                    if (cnt > 0) mbar_wait(port, (cnt - 1) & 1u);
+#endif
+#if RTK_SCORE_EXPERIMENT_NOLOAD             // timing experiment: all the arithmetic on made-up accumulators, no TMEM read
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) r[i] = 0x3f000000u + (uint32_t)(row + tb) * 0x1000u + (uint32_t)i * 0x20000u;
+#else
+                    tmem_ld64(taddr, r);
+                    tmem_ld_wait();
+#endif
+#if RTK_SCORE_PORT
+                    if (lane == 0) mbar_arrive(port);
+#endif
+#if RTK_SCORE_EARLY_RELEASE
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(t_empty(b));    // the MMA of tile cnt + 4 may overwrite the buffer now
+#endif
+                    softmax_cols<PASS, 64>(r, 0, valid, st, cq, inv, inv2, l2e2);
+                }
+#elif RTK_SCORE_X32DB
+                {   // both 32-column loads issued up front: the second is in flight while the first half is computed
+                    uint32_t ra[32], rb[32];
+                    tmem_ld32(taddr, ra);
+                    tmem_ld32(taddr + 32, rb);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 32>(ra, 0, valid, st, cq, inv, inv2, l2e2);
+                    softmax_cols<PASS, 32>(rb, 32, valid, st, cq, inv, inv2, l2e2);
+                }
+#else
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c * 32, r);
+                    tmem_ld_wait();
+                    softmax_cols<PASS, 32>(r, c * 32, valid, st, cq, inv, inv2, l2e2);
+                }
+#endif
+#if !(RTK_SCORE_EARLY_RELEASE && RTK_SCORE_X64 && !RTK_SCORE_X16)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(t_empty(b));
+#endif
+            }
+#endif
             const float m = st.m;
-            // ---- fold the two column halves and write this CTA's share of the unit
+            // ---- fold the four groups and write this CTA's share of the unit
             float a0, a1;
-            upk2(st.acc, a0, a1);
-            if (PASS == 2) { a0 = st.c0; a1 = st.c1; }
+            upk2(add2(st.acc, st.acc_b), a0, a1);
+            if (PASS == 2 && RTK_SCORE_FHADD) { a0 = st.c0 + st.c2; a1 = st.c1 + st.c3; }
             const int part = (tb0 == 0) ? 0 : 1;
             const bool whole = (tb0 == 0) && (tb1 == nt);
             const size_t o = (size_t)h * nt * kTile + (size_t)ta * kTile + row;
-            const int g_lo = grp & ~1;               // the two groups of this stationary tile
+            // groups that fold into one row of one stationary tile: all of them, or (paired units) the two column halves
+            const int g_lo = RTK_SCORE_PAIR ? (grp & ~1) : 0, g_hi = RTK_SCORE_PAIR ? g_lo + 2 : kGroups;
             const bool folder = (grp == g_lo) && has_tile;
             if (PASS == 1) {
                 merge[(grp * kTile + row) * 2] = m;
@@ -503,9 +820,9 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                 asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
                 if (folder) {
                     float mn = -INFINITY;
-                    for (int g = g_lo; g < g_lo + 2; ++g) mn = fmaxf(mn, merge[(g * kTile + row) * 2]);
+                    for (int g = g_lo; g < g_hi; ++g) mn = fmaxf(mn, merge[(g * kTile + row) * 2]);
                     float lt = 0.f;
-                    for (int g = g_lo; g < g_lo + 2; ++g) {
+                    for (int g = g_lo; g < g_hi; ++g) {
                         const float mg = merge[(g * kTile + row) * 2];
                         if (mg > -INFINITY) lt += merge[(g * kTile + row) * 2 + 1] * ex2f((mg - mn) * kLog2e);
                     }
@@ -517,7 +834,8 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                 merge[grp * kTile + row] = a0 + a1;
                 asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
                 if (folder) {
-                    const float cs = merge[g_lo * kTile + row] + merge[(g_lo + 1) * kTile + row];
+                    float cs = merge[g_lo * kTile + row];
+                    for (int g = g_lo + 1; g < g_hi; ++g) cs += merge[g * kTile + row];
                     prm.colsum_part[(size_t)part * hl + o] = cs;
                     if (whole) prm.colsum_part[hl + o] = 0.f;
                 }
@@ -686,7 +1004,6 @@ int pivot_score_batch(const ScoreBatch& b, void* workspace, size_t workspace_byt
 extern "C" int rtk_pivot_score(const void* q, int64_t H, int64_t q_stride_h, int64_t q_stride_l, const void* k, int64_t KVH,
                                int64_t k_stride_h, int64_t k_stride_l, int64_t L, int64_t D, void* head_scores,
                                void* workspace, size_t workspace_bytes, void* stream) {
-    RTK_NVTX("rtk_pivot_score");
     if (!q || !k || !head_scores || !workspace || H < 1 || KVH < 1 || L < 1) return RTK_E_BADARG;
     ScoreBatch b = {};
     b.n = 1; b.H = H; b.KVH = KVH; b.L = L; b.D = D;

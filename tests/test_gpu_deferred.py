@@ -185,3 +185,89 @@ def test_deferred_opaque_rotary_falls_back_to_immediate(monkeypatch):
     for layer in range(2):
         assert torch.equal(a.layers[layer].keys, b.layers[layer].keys)
         assert torch.equal(a.position_cache[layer], b.position_cache[layer])
+
+
+def test_deferred_with_positions_rebased_in_place_per_layer():
+    """the Qwen2-VL attention forward re-bases ONE shared position tensor in place for every layer
+    (`pos3d[0, 0, :] += prev + 1 - pos3d[0, 0, 0]`, reference qwen2_vl.py:68-73).  Deferred compression reads the ids at
+    after_forward(), so it must have kept its own copy: layers whose `prev` differ would otherwise all be un-rotated and
+    re-indexed with the LAST layer's ids."""
+    lc = _lc()
+    H, KVH, L, D, layers, chunks, ratio, mrope = 4, 2, 256, 64, 4, 3, 0.1, [8, 12, 12]
+    rot = TableRotary(D, mrope=True)
+    rot.inv_freq = rot.inv_freq.cuda()
+
+    def run(deferred):
+        cfg = _cfg(H, KVH, D, layers, ratio, True)
+        cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"] = deferred
+        cache = lc.PivotKVCache(cfg)
+        prevs = []
+        for c in range(chunks):
+            cache.kvcache_compression = True
+            shared = _positions(L, 1000 * c, mrope, n_tok=16).contiguous()       # one tensor for all layers of the chunk
+            row = []
+            for layer in range(layers):
+                q, k, v = qkv(H, KVH, L, D, 3.0, seed=77 * c + layer)
+                prev = cache.get_prev_temporal_idx(layer)
+                row.append(int(prev))
+                shared[0, 0, :] += prev + 1 - shared[0, 0, 0]
+                cache.update(k, v, layer, {"query_states": q, "position_ids": shared, "rotary_emb": rot,
+                                           "mrope_section": mrope})
+            prevs.append(row)
+            cache.after_forward()
+        return cache, prevs
+
+    a, pa = run(False)
+    b, pb = run(True)
+    assert pa == pb
+    assert any(len(set(row)) > 1 for row in pa[1:]), "the layers must disagree on `prev` for this test to mean anything"
+    for layer in range(layers):
+        assert torch.equal(a.position_cache[layer], b.position_cache[layer])
+        assert torch.equal(a.layers[layer].keys, b.layers[layer].keys)
+        assert torch.equal(a.layers[layer].values, b.layers[layer].values)
+
+
+def test_single_layer_growth_keeps_the_pending_overwrite():
+    """the same layer updated chunk after chunk with no after_forward() in between (1-layer model / direct cache
+    API use): when the buffer grows past its 8192-row capacity the previous chunk's kept rows must already be in place
+    before the old buffer is copied"""
+    lc = _lc()
+    H, KVH, L, D, ratio = 4, 2, 1024, 64, 0.9
+    cfg = _cfg(H, KVH, D, 1, ratio, False)
+    cache = lc.PivotKVCache(cfg)
+    want_k, want_v = [], []
+    for c in range(10):                                               # 9 x 921 kept rows + 1024 crosses 8192 at chunk 9
+        q, k, v = qkv(H, KVH, L, D, 3.0, seed=300 + c)
+        cache.kvcache_compression = True
+        ko, vo = cache.update(k, v, 0, {"query_states": q, "position_ids": _positions(L, 0, None)})
+        idx = cache.last_keep_indices.long()
+        want_k.append(k[:, :, idx])
+        want_v.append(v[:, :, idx])
+        past = sum(t.shape[2] for t in want_k[:-1])
+        assert torch.equal(ko[:, :, :past], torch.cat(want_k[:-1], 2)) if past else True      # what this step's attention sees
+    assert cache.layers[0]._kbuf.shape[2] > 8192
+    assert torch.equal(cache.layers[0].keys, torch.cat(want_k, 2))
+    assert torch.equal(cache.layers[0].values, torch.cat(want_v, 2))
+    # and through the bare layer API
+    layer = lc.PivotKVLayer()
+    ks = []
+    for c in range(10):
+        _, k, v = qkv(H, KVH, L, D, 1.0, seed=400 + c)
+        k_all, _ = layer.update(k, v)
+        assert k_all.shape[2] == sum(t.shape[2] for t in ks) + L
+        layer.replace_tail(L, k[:, :, :900].contiguous(), v[:, :, :900].contiguous())
+        ks.append(k[:, :, :900])
+    assert torch.equal(layer.keys, torch.cat(ks, 2))
+
+
+def test_deferred_unsupported_shape_takes_the_immediate_path():
+    """a shape outside the batched kernels' envelope (here D = 32) must not touch the cache state before the
+    library refuses it"""
+    lc = _lc()
+    cfg = _cfg(4, 2, 32, 1, 0.5, False)
+    cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"] = True
+    cache = lc.PivotKVCache(cfg)
+    q, k, v = qkv(4, 2, 128, 32, 1.0, seed=1)
+    with pytest.raises(Exception):
+        cache.update(k, v, 0, {"query_states": q, "position_ids": _positions(128, 0, None)})
+    assert not cache._deferred and cache.layers[0]._deferred_owner is None

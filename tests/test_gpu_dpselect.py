@@ -189,3 +189,38 @@ def test_full_size_config4_llava_shape():
         out, mask, idx = vc.memory_bank_compress_keyframe(x[None], t, 3, sync=sync, return_indices=True)
         want_out, want_mask, want_idx = ro.dpselect(x[None], t, sync)
         assert torch.equal(idx.long(), want_idx) and torch.equal(mask, want_mask) and torch.equal(out, want_out)
+
+
+def _synthetic_video(T, N, C, seed):
+    """scene-structured bf16 video built ON the GPU (scenes of 3..40 grids + 0.3 noise, every 9th grid an exact duplicate)"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.empty(T, N, C, dtype=torch.bfloat16, device="cuda")
+    t = 0
+    while t < T:
+        run = min(T - t, 3 + (seed * 7 + t * 13) % 38)
+        scene = torch.randn(N, C, generator=g, device="cuda")
+        x[t:t + run] = (scene[None] + 0.3 * torch.randn(run, N, C, generator=g, device="cuda")).to(torch.bfloat16)
+        t += run
+    x[9::9] = x[8:-1:9][: x[9::9].shape[0]]
+    return x
+
+
+@pytest.mark.parametrize("T,N,C,cases", [
+    (1024, 256, 3584, ((1024, False), (512, False), (256, False), (512, True))),      # the 2048-frame headline video
+    (2048, 729, 1152, ((2048, False), (1024, False), (512, True))),                   # BASELINE config 4: LLaVA-Video, 2048 frames
+])
+def test_headline_sizes_bit_exact_vs_reference_ops(T, N, C, cases):
+    """DPSelect at the benchmark's own sizes (T = 1024 Qwen2-VL grids, T = 2048 LLaVA frames): distances,
+    kept indices, masks and compacted embeddings equal the reference's torch-CUDA op sequence bit for bit"""
+    from oracle import reference_ops as ro
+    vc = _mods()
+    x = _synthetic_video(T, N, C, 3)
+    assert torch.equal(vc.dpselect_distance(x), ref_dis_cuda(x))
+    for t, sync in cases:
+        out, mask, idx = vc.memory_bank_compress_keyframe(x[None], t, 3, sync=sync, return_indices=True)
+        r_out, r_mask, r_idx = ro.dpselect(x[None], t, sync)
+        assert torch.equal(idx.long(), r_idx), (T, t, sync)
+        assert torch.equal(mask, r_mask)
+        assert torch.equal(out, r_out)
+        assert out.shape == (1, t, N, C) and mask.shape == (t * N,)
+        del out, r_out

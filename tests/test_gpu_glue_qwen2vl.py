@@ -171,3 +171,36 @@ def test_mallm_visual_compression_methods(patched, method):
     want_len = 6 + 2 * 32 + 7
     assert [o.past_key_values.get_seq_length(l) for l in range(2)] == [want_len, want_len]
     assert torch.isfinite(o.logits.float()).all()
+
+
+def test_decode_positions_follow_the_original_prompt_with_visual_ratio_below_one(patched):
+    """with DPSelect ratio < 1 the first decoded token must sit right after the largest prompt position
+    (`cache_position[0] + rope_deltas`, both counted on the ORIGINAL prompt - reference qwen2_vl.py:583-589), not
+    `num_token_diff` positions earlier"""
+    model = tiny_model()
+    inp = make_inputs()
+    model.config.longvideo_kwargs = lv_kwargs(rv=0.5, rkv=0.5, reforge=True, chunk_frames=8)
+    seen = []
+    orig_lm = patched._lm
+
+    def spy(self, cache, inputs_embeds, position_ids, **kw):
+        seen.append(position_ids.clone())
+        return orig_lm(self, cache, inputs_embeds, position_ids, **kw)
+
+    patched._lm = spy
+    try:
+        gen_cfg = copy.deepcopy(model.generation_config)
+        gen_cfg.do_sample = False
+        with torch.no_grad():
+            model.generate(**inp, max_new_tokens=3, generation_config=gen_cfg)
+    finally:
+        patched._lm = orig_lm
+    full_pos, delta = patched.mrope_position_ids(inp["input_ids"], VIDEO_ID, inp["video_grid_thw"], 2)
+    decode = [p for p in seen if p.shape[-1] == 1]
+    assert len(decode) == 2                                         # 3 new tokens = prefill + 2 decode steps
+    want_first = int(full_pos.max()) + 1                            # = S_orig + rope_delta
+    assert want_first == inp["input_ids"].shape[1] + int(delta)
+    prefill_last = max(int(p.max()) for p in seen if p.shape[-1] > 1)
+    for i, p in enumerate(decode):
+        assert p.shape == (3, 1, 1) and p.flatten().tolist() == [want_first + i] * 3
+    assert int(decode[0].min()) > prefill_last

@@ -466,6 +466,7 @@ int dpselect_sim_nrm(const void* x, int64_t T, int64_t N, int64_t C, DisAux aux,
 using namespace rtk;
 
 extern "C" int rtk_dpselect_dis(const void* x, int64_t T, int64_t N, int64_t C, int halo, float* dis, void* stream) {
+    RTK_NVTX("rtk_dpselect_dis");
     if (!x || !dis || T < 1 || N < 1) return RTK_E_BADARG;
     if (C % 8 != 0 || C < 256 || C > 8192) return RTK_E_UNSUPPORTED;
     if (((uintptr_t)x & 15u) != 0) return RTK_E_ALIGN;
@@ -490,6 +491,7 @@ extern "C" int rtk_dpselect_dis(const void* x, int64_t T, int64_t N, int64_t C, 
 
 extern "C" int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64_t t, int sync, int32_t* idx,
                                    uint8_t* mask, void* stream) {
+    RTK_NVTX("rtk_dpselect_select");
     if (!dis || !idx || !mask || T < 1 || N < 1 || t < 1 || t > T) return RTK_E_BADARG;
     if (T > 8192) return RTK_E_UNSUPPORTED;
     cudaStream_t st = (cudaStream_t)stream;
@@ -516,6 +518,7 @@ extern "C" int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64
 
 extern "C" int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t C, const int32_t* idx, int64_t t,
                                    int sync, void* out, void* stream) {
+    RTK_NVTX("rtk_dpselect_gather");
     if (!x || !idx || !out || T < 1 || N < 1 || C < 1 || t < 1) return RTK_E_BADARG;
     if (C % 8 != 0) return RTK_E_UNSUPPORTED;
     if ((((uintptr_t)x | (uintptr_t)out) & 15u) != 0) return RTK_E_ALIGN;
@@ -541,6 +544,7 @@ extern "C" int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t 
 
 extern "C" int rtk_gather_rows(const void* x, int64_t row_bytes, const int64_t* src_row, int64_t rows, void* out,
                                void* stream) {
+    RTK_NVTX("rtk_gather_rows");
     if (!x || !src_row || !out || rows < 0 || row_bytes < 16) return RTK_E_BADARG;
     if (row_bytes % 16 != 0) return RTK_E_UNSUPPORTED;
     if ((((uintptr_t)x | (uintptr_t)out) & 15u) != 0) return RTK_E_ALIGN;

@@ -738,6 +738,7 @@ extern "C" size_t rtk_mallm_workspace_bytes(int64_t T, int64_t N, int64_t C, int
 extern "C" int rtk_mallm_compress(const void* x, const void* sizes_in, int64_t T, int64_t N, int64_t C, int64_t t, int sync,
                                   int hard, void* out, void* sizes_out, void* workspace, size_t workspace_bytes,
                                   void* stream_) {
+    RTK_NVTX("rtk_mallm_compress");
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!x || !out || !workspace || T < 1 || N < 1 || t < 1 || t > T) return RTK_E_BADARG;
     if (C % 8 != 0 || C < 256 || C > 8192 || T > 8192 || N > 65535) return RTK_E_UNSUPPORTED;

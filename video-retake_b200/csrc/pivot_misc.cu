@@ -584,6 +584,11 @@ using namespace rtk;
 
 extern "C" int rtk_version(void) { return RTK_ABI_VERSION; }
 
+#ifndef RTK_BUILD_ID
+#define RTK_BUILD_ID "unknown"
+#endif
+extern "C" const char* rtk_build_id(void) { return RTK_BUILD_ID; }
+
 extern "C" int64_t rtk_launch_count(void) { return (int64_t)rtk::g_launches; }
 
 extern "C" const char* rtk_error_string(int code) {
@@ -603,6 +608,7 @@ extern "C" int rtk_pivot_rope(const void* x, int64_t heads, int64_t L, int64_t D
                               const void* cos, const void* sin, int n_pos, const int32_t* mrope_section_host,
                               float inv_scale2, int forward, void* out, int64_t out_stride_h, int64_t out_stride_l,
                               void* stream) {
+    RTK_NVTX("rtk_pivot_rope");
     if (!x || !cos || !sin || !out || heads < 1 || L < 1 || D < 16) return RTK_E_BADARG;
     if (D % 16 != 0 || (n_pos != 1 && n_pos != 3)) return RTK_E_UNSUPPORTED;
     if (n_pos == 3 && !mrope_section_host) return RTK_E_BADARG;
@@ -629,6 +635,7 @@ extern "C" int rtk_pivot_rope(const void* x, int64_t heads, int64_t L, int64_t D
 
 extern "C" int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L, const uint8_t* keymask, int64_t keep,
                                 int32_t* keep_idx, void* score_out, void* stream) {
+    RTK_NVTX("rtk_pivot_select");
     if (!head_scores || !keep_idx || KVH < 1 || L < 1 || keep < 1 || keep > L) return RTK_E_BADARG;
     if (L > 16384) return RTK_E_UNSUPPORTED;
     const size_t smem = (size_t)L * 4 + 112 * 4;
@@ -647,6 +654,7 @@ extern "C" int rtk_pivot_compact(const void* k, const void* v, int64_t KVH, int6
                                  int64_t stride_l, const int32_t* keep_idx, int64_t keep, void* k_out, void* v_out,
                                  int64_t out_stride_h, const int64_t* pos, int n_pos, int64_t* pos_out, int reforge,
                                  void* stream) {
+    RTK_NVTX("rtk_pivot_compact");
     return compact_kv(k, v, KVH, L, D, stride_h, stride_l, stride_h, stride_l, keep_idx, keep, k_out, v_out, out_stride_h, pos,
                       n_pos, pos_out, reforge, stream);
 }
@@ -676,6 +684,7 @@ static int compact_kv(const void* k, const void* v, int64_t KVH, int64_t L, int6
 extern "C" int rtk_pivot_rope_tables(const int64_t* pos, int n_pos, int64_t L, int64_t D, const float* inv_freq,
                                      const int32_t* mrope_section_host, float attention_scaling, void* cos_out,
                                      void* sin_out, void* stream) {
+    RTK_NVTX("rtk_pivot_rope_tables");
     if (!pos || !inv_freq || !cos_out || !sin_out || L < 1 || D < 2) return RTK_E_BADARG;
     if (D % 2 != 0 || (n_pos != 1 && n_pos != 3)) return RTK_E_UNSUPPORTED;
     if (n_pos == 3 && !mrope_section_host) return RTK_E_BADARG;
@@ -731,6 +740,7 @@ extern "C" size_t rtk_pivot_update_workspace_bytes(int64_t H, int64_t KVH, int64
 }
 
 extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
+    RTK_NVTX("rtk_pivot_update");
     if (!a || !a->q || !a->k || !a->v || !a->k_out || !a->v_out || !a->keep_idx || !a->head_scores || !a->workspace)
         return RTK_E_BADARG;
     if (a->workspace_bytes < rtk_pivot_update_workspace_bytes(a->H, a->KVH, a->L, a->D)) return RTK_E_WORKSPACE;
@@ -917,6 +927,7 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
 
 extern "C" int rtk_pivot_update_batch(const rtk_pivot_update_args* layers, int64_t n_layers, void* workspace,
                                       size_t workspace_bytes, void* stream) {
+    RTK_NVTX("rtk_pivot_update_batch");
     if (!layers || n_layers < 1 || !workspace) return RTK_E_BADARG;
     const rtk_pivot_update_args& a0 = layers[0];
     if (a0.H < 1 || a0.KVH < 1 || a0.L < 1 || a0.keep < 1 || a0.keep > a0.L) return RTK_E_BADARG;
@@ -950,6 +961,7 @@ extern "C" int rtk_pivot_update_batch(const rtk_pivot_update_args* layers, int64
 extern "C" int rtk_kv_block_copy(int n_jobs, const void* const* src, void* const* dst, const int64_t* heads, const int64_t* rows,
                                  const int64_t* src_stride_h, const int64_t* src_stride_l, const int64_t* dst_stride_h,
                                  const int64_t* dst_stride_l, int64_t D, void* stream) {
+    RTK_NVTX("rtk_kv_block_copy");
     if (n_jobs < 1 || n_jobs > 4 || !src || !dst || !heads || !rows || D < 8) return RTK_E_BADARG;
     if (D % 8 != 0) return RTK_E_UNSUPPORTED;
     CopyJobs j;

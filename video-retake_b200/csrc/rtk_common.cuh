@@ -4,6 +4,7 @@
 
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 #include <stdint.h>
 
 #include "../../include/rtk_b200.h"
@@ -20,6 +21,16 @@ extern long long g_launches;  // host-side launch counter (rtk_launch_count)
     } while (0)
 
 constexpr int kWarp = 32;
+
+// NVTX range covering one C-ABI call on the host thread (ranges at the kernel entry points).
+// nvtx3 is header-only and binds to the profiler's injection library lazily: without a profiler push / pop are no-ops.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+#define RTK_NVTX(name) ::rtk::NvtxRange nvtx_range__(name)
 
 // optional outputs of the streaming cosine kernel (dpselect.cu) used by the MA-LLM compressors (mallm.cu):
 // sim[i * si + p * sp] = bf16 cosine(frame i, frame i + 1), nrm[i * si + p * sp] = clamped bf16 norm of frame i

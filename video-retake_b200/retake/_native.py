@@ -34,6 +34,7 @@ def lib() -> C.CDLL:
     p, i64, i32, f32, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_size_t
     sig = {
         "rtk_version": ([], C.c_int),
+        "rtk_build_id": ([], C.c_char_p),
         "rtk_error_string": ([C.c_int], C.c_char_p),
         "rtk_launch_count": ([], i64),
         "rtk_dpselect_dis": ([p, i64, i64, i64, i32, p, p], C.c_int),
@@ -59,11 +60,41 @@ def lib() -> C.CDLL:
         fn.argtypes, fn.restype = args, res
     if L.rtk_version() != ABI_VERSION:
         raise RtkError(f"ABI mismatch: library reports version {L.rtk_version()}, binding expects {ABI_VERSION}")
+    _check_build_id(L)
     _lib = L
     return L
 
 
-EXPORTS = ("rtk_version", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
+def _source_id():
+    """id of the sources lying next to this package (None when the tree ships without them)"""
+    import importlib.util
+    path = os.path.join(os.path.dirname(_HERE), "build.py")
+    if not os.path.exists(path) or not os.path.isdir(os.path.join(os.path.dirname(_HERE), "csrc")):
+        return None
+    spec = importlib.util.spec_from_file_location("rtk_build_for_id", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.source_id()
+
+
+def _check_build_id(L) -> None:
+    """the in-tree library must have been built from the in-tree sources (the build used to be gated on file
+    times, so nothing proved which sources a record came from).  RTK_B200_LIB (an explicitly chosen library, e.g. an A/B
+    variant) and RTK_ALLOW_STALE_LIB=1 skip the check."""
+    if "RTK_B200_LIB" in os.environ or os.environ.get("RTK_ALLOW_STALE_LIB") == "1":
+        return
+    want = _source_id()
+    got = L.rtk_build_id().decode()
+    if want is not None and got != want:
+        raise RtkError(f"{LIB_PATH} was built from other sources (library id {got}, sources {want}): "
+                       "run `python video-retake_b200/build.py`")
+
+
+def build_id() -> str:
+    return lib().rtk_build_id().decode()
+
+
+EXPORTS = ("rtk_version", "rtk_build_id", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
            "rtk_dpselect_gather", "rtk_gather_rows", "rtk_mallm_workspace_bytes", "rtk_mallm_compress", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
            "rtk_pivot_select", "rtk_pivot_compact", "rtk_pivot_rope_tables", "rtk_pivot_update_workspace_bytes",
            "rtk_pivot_update", "rtk_pivot_update_batch_workspace_bytes", "rtk_pivot_update_batch", "rtk_kv_block_copy")

@@ -232,6 +232,7 @@ def retake_LlavaOnevisionModel_forward(self, input_ids=None, pixel_values=None, 
                 else self.config.vision_feature_select_strategy)
 
     batch_size, frames = pixel_values_videos.shape[:2]
+    prompt_tokens = input_ids.shape[1]        # BEFORE visual compression: what generate() derives decode positions from
     position_ids = torch.arange(input_ids.shape[1], device=input_ids.device)[None]
     feats = _siglip_features(self, pixel_values_videos, vision_feature_layer)                 # [T, N, C]
     input_ids, attention_mask, feats, position_ids, _, frames, keypatches_mask = self.compress_video_tokens(
@@ -279,7 +280,9 @@ def retake_LlavaOnevisionModel_forward(self, input_ids=None, pixel_values=None, 
                     cache.after_forward()
             cache.keypatches_mask_chunk = None
             cache.kvcache_compression = False
-    cache.retake_seen_tokens = input_ids.shape[1]
+    # generate() numbers decoded tokens from the ORIGINAL prompt length (attention-mask cumsum / cache_position), not from
+    # the sequence DPSelect / MA-LLM shortened (reference llava_onevision.py:262-265 only trims the prefill ids)
+    cache.retake_seen_tokens = prompt_tokens
     return hf.LlavaOnevisionModelOutputWithPast(last_hidden_state=outputs.last_hidden_state, past_key_values=cache)
 
 

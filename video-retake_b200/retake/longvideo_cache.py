@@ -374,8 +374,10 @@ class PivotKVLayer(DynamicLayer):
 
     def update(self, key_states, value_states, *args, **kwargs):
         """append in place, return views ``[past | new]``"""
-        jobs = self.pending_jobs()
+        # room first: if the buffer has to grow, append_jobs settles the pending overwrite into the OLD buffer before it
+        # is copied; popping the pending jobs earlier would leave them pointing at the discarded buffer
         more, k_all, v_all = self.append_jobs(key_states, value_states)
+        jobs = self.pending_jobs()
         _block_copy(jobs + more)
         return k_all, v_all
 
@@ -506,21 +508,25 @@ class PivotKVCache(DynamicCache):
         groups: Dict[Any, List[Dict[str, Any]]] = {}
         for e in pend:
             groups.setdefault(e["sig"], []).append(e)
-        for sig, entries in groups.items():
-            H, KVH, L, D = sig[:4]
-            dev = entries[0]["device"]
-            n = len(entries)
-            arr = (_UpdateArgs * n)(*[e["args"] for e in entries])
-            ws = _workspace(dev, int(lib.rtk_pivot_update_batch_workspace_bytes(H, KVH, L, D, n)) + 256)
-            ws_ptr = (ws.data_ptr() + 255) & ~255
-            if self.score_events is not None:
-                arr[0].ev_score_begin, arr[0].ev_score_end = self.score_events
-                self.score_events = None
-            with torch.cuda.device(dev):
-                N.check(lib.rtk_pivot_update_batch(arr, n, ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()), N.stream_ptr(dev)),
-                        "rtk_pivot_update_batch")
-        for e in pend:
-            e["layer"]._deferred_owner = None
+        try:
+            for sig, entries in groups.items():
+                H, KVH, L, D = sig[:4]
+                dev = entries[0]["device"]
+                n = len(entries)
+                arr = (_UpdateArgs * n)(*[e["args"] for e in entries])
+                ws = _workspace(dev, int(lib.rtk_pivot_update_batch_workspace_bytes(H, KVH, L, D, n)) + 256)
+                ws_ptr = (ws.data_ptr() + 255) & ~255
+                if self.score_events is not None:
+                    arr[0].ev_score_begin, arr[0].ev_score_end = self.score_events
+                    self.score_events = None
+                with torch.cuda.device(dev):
+                    N.check(lib.rtk_pivot_update_batch(arr, n, ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr()),
+                                                       N.stream_ptr(dev)), "rtk_pivot_update_batch")
+        finally:
+            # whatever happened, no layer may keep pointing at a batch that will never run again (a failed launch
+            # raises to the caller; a later read of the cache must not recurse into this queue)
+            for e in pend:
+                e["layer"]._deferred_owner = None
 
     def update_num_evicted_tokens(self, num_tokens: int, layer_idx: int) -> int:
         while len(self.num_evicted_tokens) <= layer_idx:
@@ -568,7 +574,7 @@ class PivotKVCache(DynamicCache):
 
     # ------------------------------------------------------------------------------------------------ update
     def _update_args(self, query_states, key_states, value_states, position_ids, rotary_emb_fn, mrope_section, keep_len,
-                     k_out=None, v_out=None, pos_out=None):
+                     k_out=None, v_out=None, pos_out=None, own_pos=False):
         """fill one ``rtk_pivot_update_args``; returns (args, outputs, tensors that must outlive the launches, fast)
         ``k_out`` / ``v_out`` ``[1, KVH, keep, D]`` (rows D apart, any head stride) and ``pos_out`` ``[..., keep]`` default to
         fresh tensors; ``fast`` is False when the rotary module is opaque (tables come from calling it)"""
@@ -601,7 +607,9 @@ class PivotKVCache(DynamicCache):
         pos_flat = cos = sin = inv = None
         if position_ids is not None:
             N.require_cuda(position_ids, "position_ids", torch.int64)
-            pos_flat = position_ids.reshape(-1, L).contiguous()
+            # own_pos (deferred launches): the ids are read at after_forward(), by which time the caller may have
+            # re-based the SAME tensor in place for the next layers (the attention forward does) - keep a private copy
+            pos_flat = position_ids.reshape(-1, L).clone() if own_pos else position_ids.reshape(-1, L).contiguous()
             a.n_pos, a.pos = pos_flat.shape[0], pos_flat.data_ptr()
             if pos_out is None:
                 pos_out = torch.empty(position_ids.shape[:-1] + (keep_len,), dtype=torch.int64, device=dev)
@@ -670,13 +678,19 @@ class PivotKVCache(DynamicCache):
         """queue this layer's compression for the batched call; False when it has to run now (opaque rotary module)"""
         if self.pos_embed_reforge and _rotary_inv_freq(rotary_emb_fn) is None:
             return False
+        # the batched kernels' envelope (rtk_pivot_update_batch): outside it the chunk takes the immediate path, whose
+        # C-ABI call reports the problem BEFORE any cache state has changed
+        H, KVH, D = query_states.shape[1], key_states.shape[1], query_states.shape[3]
+        if (query_states.shape[2] > 16384 or D not in (64, 128) or H % KVH != 0 or query_states.dtype != torch.bfloat16
+                or key_states.shape[2] != query_states.shape[2]):
+            return False
         q_len = query_states.shape[2]
         pos_out = None
         if self.pos_embed_reforge:
             pos_out = self._position_slots(position_ids, keep_len, layer_idx)      # kept positions land in the position cache
         k_dst, v_dst = layer.shrink_tail(q_len, keep_len, self)                    # kept rows land in the cache itself
         a, outs, keepalive, _, sig = self._update_args(query_states, key_states, value_states, position_ids, rotary_emb_fn,
-                                                       mrope_section, keep_len, k_dst, v_dst, pos_out)
+                                                       mrope_section, keep_len, k_dst, v_dst, pos_out, own_pos=True)
         self._deferred.append({"args": a, "outs": outs, "keepalive": keepalive, "sig": sig, "layer": layer,
                                "device": query_states.device})
         self._last_head_scores, self._last_keep_indices = outs["head_scores"], outs["keep_idx"]
@@ -701,9 +715,10 @@ class PivotKVCache(DynamicCache):
         layer = self.layers[layer_idx]
         if layer._deferred_owner is not None:
             self.flush_deferred()                       # no after_forward() since this layer's last chunk: settle it now
+        # (room first - see PivotKVLayer.update: a growing buffer settles this layer's own pending overwrite itself)
+        more, key_states_output, value_states_output = layer.append_jobs(key_states, value_states)
         dirty, self._dirty = self._dirty, []
         jobs = [j for l in dirty for j in l.pending_jobs()]
-        more, key_states_output, value_states_output = layer.append_jobs(key_states, value_states)
         _block_copy(jobs + more)
 
         if self.kvcache_compression:

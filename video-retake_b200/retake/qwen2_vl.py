@@ -260,6 +260,7 @@ def retake_Qwen2VLModel_forward(self, input_ids=None, attention_mask=None, posit
     position_ids, delta = mrope_position_ids(input_ids, self.config.video_token_id, video_grid_thw,
                                              self.config.vision_config.spatial_merge_size)
     self.rope_deltas = delta
+    prompt_tokens = input_ids.shape[1]        # BEFORE visual compression: what generate()'s cache_position counts
     video_embeds = _video_features(self, pixel_values_videos, video_grid_thw)
     input_ids, attention_mask, video_embeds, _, position_ids, _, keypatches_mask = self.compress_video_tokens(
         input_ids=input_ids, attention_mask=attention_mask, video_embeds=video_embeds, cache_position=None,
@@ -297,7 +298,10 @@ def retake_Qwen2VLModel_forward(self, input_ids=None, attention_mask=None, posit
                     cache.after_forward()
             cache.keypatches_mask_chunk = None
             cache.kvcache_compression = False          # turned off for the trailing text and for decoding
-    cache.retake_seen_tokens = input_ids.shape[1]
+    # decode positions are `cache_position[0] + rope_deltas` in the reference (qwen2_vl.py:583-589): both count the
+    # ORIGINAL prompt, not the sequence DPSelect / MA-LLM shortened, so the first generated token sits right after the
+    # largest prompt position whatever the visual ratio is
+    cache.retake_seen_tokens = prompt_tokens
     return hf.Qwen2VLModelOutputWithPast(last_hidden_state=outputs.last_hidden_state, past_key_values=cache,
                                          rope_deltas=self.rope_deltas)
 
