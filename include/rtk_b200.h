@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RTK_ABI_VERSION 2
+#define RTK_ABI_VERSION 3
 
 #define RTK_E_BADARG      (-1)  /* null pointer / non-positive size                         */
 #define RTK_E_ALIGN       (-2)  /* pointer or stride not 16-byte aligned                    */
@@ -76,11 +76,18 @@ int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64_t t, int s
 
 /* Stream compaction of the surviving rows; replaces visual_compression.py:138 / :173.
  *   out[j, p, :] = x[idx[j, p], p, :] (sync=0)   or   x[idx[j], p, :] (sync=1);  out bf16 [t, N, C]
- *   idx must be strictly ascending along j (what rtk_dpselect_select writes); t == T is therefore the identity and is
- *   served by one device-to-device copy.
+ *   t == T (compression_ratio 1.0, the shipped recipe) is the identity; it runs through the same kernel.
  */
 int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t C, const int32_t* idx, int64_t t,
                         int sync, void* out, void* stream);
+
+/* Frame-range split of ONE video over the GPUs of a box: the compaction of visual_compression.py:138 / :173
+ * restricted to the frames a rank owns.  x_local holds frames [frame_first, frame_first + frames_local) of the video (bf16
+ * [frames_local, N, C]); idx is the replicated result of rtk_dpselect_select on the all-gathered distances; only the rows of
+ * out (bf16 [t, N, C], the reference's layout) whose source frame lies in [t0, t1) are written - the other rows belong to
+ * other ranks and are left untouched.  No host synchronisation, no index arithmetic in torch. */
+int rtk_dpselect_gather_owned(const void* x_local, int64_t frames_local, int64_t frame_first, int64_t t0, int64_t t1,
+                              int64_t N, int64_t C, const int32_t* idx, int64_t t, int sync, void* out, void* stream);
 
 /* Generic row gather out[i, :] = x[src_row[i], :] (rows of row_bytes, a multiple of 16).  Used when DPSelect is split
  * by frame range across GPUs: every rank compacts only the survivors it owns (visual_compression.py:173 restricted
@@ -201,6 +208,23 @@ typedef struct rtk_pivot_update_args {
     void* workspace; size_t workspace_bytes;
     void* ev_score_begin; void* ev_score_end;                   /* optional cudaEvent_t pair recorded around the scoring   */
     int64_t pos_out_stride;                                     /* row stride of pos_out in elements; 0 = keep (ABI 2)     */
+    /* ---- ABI 3: the KV-head split of ONE video over the GPUs of a box as two calls around one exchange.
+     * Call 1 (skip_select = 1) scores this rank's KV heads; call 2 (skip_score = 1) selects on the rows of EVERY rank and
+     * compacts this rank's heads.  Call 2 must follow call 1 with the same arguments and workspace (the un-rotated K copy of
+     * call 1 is compacted).  The exchange in between is either the caller's own collective (xchg_world = 0: e.g. one NCCL
+     * all_gather_into_tensor) or done by the library over peer-mapped memory (xchg_world > 1, below).                        */
+    int32_t skip_score;                                         /* 1: head_scores is an INPUT, bf16 [score_rows, L]       */
+    int32_t score_rows;                                         /* rows averaged by the select (0: KVH)                    */
+    /* Peer exchange (NVLink P2P stores, no collective launch): xchg_scores[r] is rank r's bf16 [score_rows, L] buffer and
+     * xchg_flags[r] its uint32[8] flag words, both mapped into this process (CUDA IPC / symmetric memory).  Call 1 expects
+     * head_scores == (bf16*)xchg_scores[xchg_rank] + xchg_rank * KVH * L, copies those rows into the same rows of every
+     * peer's buffer and then stores xchg_epoch into xchg_flags[r][xchg_rank] for every r (release, system scope).  Call 2
+     * expects head_scores == xchg_scores[xchg_rank]; its select kernel first waits until all xchg_world words of
+     * xchg_flags[xchg_rank] equal xchg_epoch.  Use two buffer / flag sets alternately (a rank may be one update ahead).     */
+    int32_t xchg_world, xchg_rank;
+    uint32_t xchg_epoch;
+    void* xchg_scores[8];
+    uint32_t* xchg_flags[8];
 } rtk_pivot_update_args;
 
 size_t rtk_pivot_update_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D);
@@ -216,7 +240,10 @@ int rtk_pivot_update(const rtk_pivot_update_args* args, void* stream);
  * and strides are per layer; k_out / v_out may point straight into the layer's cache (rows D apart, heads out_stride_h
  * apart) and pos_out into its position cache (rows pos_out_stride apart).  layers[i].workspace is ignored; `workspace`
  * (256-byte aligned) holds the un-rotated Q / K copies and the row statistics of min(n_layers, 32) layers - more layers
- * run as consecutive groups of 32.  layers[0].ev_score_begin / _end are recorded around the first group's scoring. */
+ * run as consecutive groups of 32.  layers[0].ev_score_begin / _end are recorded around the first group's scoring.
+ * The KV-head split (ABI 3 fields) works on the whole batch too: skip_select / skip_score / score_rows / xchg_world /
+ * xchg_rank / xchg_epoch must agree over the layers, every layer brings its own head_scores rows and xchg_scores buffers,
+ * layers[0].xchg_flags carries the one flag set of the call (at most 32 layers then). */
 size_t rtk_pivot_update_batch_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D, int64_t n_layers);
 int rtk_pivot_update_batch(const rtk_pivot_update_args* layers, int64_t n_layers, void* workspace, size_t workspace_bytes,
                            void* stream);

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in rtk_b200.h but not exported"
     assert sorted(_native.EXPORTS) == names
-    assert lib.rtk_version() == _native.ABI_VERSION == 2
+    assert lib.rtk_version() == _native.ABI_VERSION == 3
     assert lib.rtk_error_string(0) == b"ok"
     assert b"aligned" in lib.rtk_error_string(-2)
 

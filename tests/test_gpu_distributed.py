@@ -43,6 +43,13 @@ def _worker(rank, world, port):
                 assert torch.equal(mask, want_mask) and torch.equal(idx.long(), want_idx)
                 out = rd.assemble_compacted(rows, slots, t, N)
                 assert torch.equal(out, want_out)
+                # sync-free form: one all_gather_into_tensor, owned rows written straight into their slots
+                part, mask2, idx2 = rd.dpselect_frame_sharded_fused(x[t0 - int(t0 > 0):t1], t0, t1, T, t, sync, zero_fill=True)
+                assert torch.equal(mask2, want_mask) and torch.equal(idx2.long(), want_idx)
+                full = idx2.long() if idx2.dim() == 2 else idx2.long()[:, None].expand(-1, N)
+                own = ((full >= t0) & (full < t1))[None, :, :, None].expand_as(want_out)
+                assert torch.equal(part[own], want_out[own]) and not bool(part[~own].any())
+                assert torch.equal(rd.assemble_owned(part), want_out)
 
         H, KVH, L, D, mrope = 28, 4, 1024, 128, [16, 24, 24]
         q = torch.randn(1, L, H, D, generator=g).to(torch.bfloat16).to(dev).transpose(1, 2)
@@ -64,14 +71,45 @@ def _worker(rank, world, port):
             cache = lc.PivotKVCache(cfg)
             cache.keypatches_mask_chunk = mask
             cache.update(k, v, 0, {"query_states": q, "position_ids": pos.clone(), "rotary_emb": rot, "mrope_section": mrope})
-            kk, vv, pp, idx, hs = rd.pivot_update_kv_sharded(q[:, g0 * G:(g0 + per[0]) * G], k[:, g0:g0 + per[0]],
-                                                             v[:, g0:g0 + per[0]], keep, per, mask, pos.clone(), rot, mrope,
-                                                             reforge)
-            assert torch.equal(hs, cache.last_head_scores) and torch.equal(idx, cache.last_keep_indices)
-            assert torch.equal(kk, cache.layers[0].keys[:, g0:g0 + per[0]])
-            assert torch.equal(vv, cache.layers[0].values[:, g0:g0 + per[0]])
-            if reforge:
-                assert torch.equal(pp, cache.position_cache[0])
+            for transport in ("p2p", "nccl", "unfused"):
+                for rep in range(3):                    # several epochs: both buffer parities, flags re-used
+                    if transport == "unfused":
+                        fn = rd._pivot_update_kv_sharded_unfused
+                        extra = {}
+                    else:
+                        fn, extra = rd.pivot_update_kv_sharded, {"transport": transport}
+                    kk, vv, pp, idx, hs = fn(q[:, g0 * G:(g0 + per[0]) * G], k[:, g0:g0 + per[0]], v[:, g0:g0 + per[0]], keep,
+                                             per, mask, pos.clone(), rot, mrope, reforge, **extra)
+                    assert torch.equal(hs, cache.last_head_scores) and torch.equal(idx, cache.last_keep_indices), (transport, rep)
+                    assert torch.equal(kk, cache.layers[0].keys[:, g0:g0 + per[0]])
+                    assert torch.equal(vv, cache.layers[0].values[:, g0:g0 + per[0]])
+                    if reforge:
+                        assert torch.equal(pp, cache.position_cache[0])
+            if rank == 0:
+                ex = rd.ScoreExchange.get(None, dev, KVH, L, "p2p")
+                print("score exchange transport:", ex.transport, flush=True)
+            # all layers of a chunk at once: two batched calls around one exchange
+            if reforge and lc._rotary_inv_freq(rot) is None:
+                continue
+            n_layers = 5
+            data = []
+            for layer in range(n_layers):
+                gl = torch.Generator().manual_seed(100 + layer)
+                ql = torch.randn(1, L, H, D, generator=gl).to(torch.bfloat16).to(dev).transpose(1, 2)
+                kl = torch.randn(1, L, KVH, D, generator=gl).to(torch.bfloat16).to(dev).transpose(1, 2)
+                vl = torch.randn(1, L, KVH, D, generator=gl).to(torch.bfloat16).to(dev).transpose(1, 2)
+                ml = (torch.rand(L, generator=gl) < 0.2).to(dev) if layer % 2 == 0 else None
+                data.append((ql, kl, vl, ml))
+            want = [lc.pivot_update(ql, kl, vl, keep, ml, pos.clone(), rot, mrope, reforge) for ql, kl, vl, ml in data]
+            for transport in ("p2p", "nccl"):
+                for rep in range(2):
+                    got = rd.pivot_update_batch_kv_sharded(
+                        [(ql[:, g0 * G:(g0 + per[0]) * G], kl[:, g0:g0 + per[0]], vl[:, g0:g0 + per[0]], ml, pos.clone())
+                         for ql, kl, vl, ml in data], keep, per, rot, mrope, reforge, transport=transport)
+                    for (kk, vv, pp, idx), (wk, wv, wp, widx, _) in zip(got, want):
+                        assert torch.equal(idx, widx), (transport, rep)
+                        assert torch.equal(kk, wk[:, g0:g0 + per[0]]) and torch.equal(vv, wv[:, g0:g0 + per[0]])
+                        assert torch.equal(pp, wp)
     finally:
         dist.destroy_process_group()
 

@@ -15,6 +15,8 @@
 // A2  dpselect_select_kernel  latency-bound (<= a few MB).  Warp per patch column held in shared memory: peaks,
 //     key = dis + 2*peak, bitwise descent for the t-th largest radix key, ordered emission with ATen's tie rule.
 // A3  dpselect_gather_kernel  HBM-bound row gather (stream compaction of surviving tokens).
+#include <climits>
+
 #include "rtk_common.cuh"
 
 namespace rtk {
@@ -399,9 +401,11 @@ dpselect_select_sync_kernel(const float* __restrict__ dis, int T, int N, int t, 
 
 // ============================================================================================== A3: gather
 // out[j, p, :] = x[idx[...], p, :]; one warp per output row, 16-byte vectors, 8 loads in flight per lane.
+// Frame-range split: x holds frames [frame_first, ...) of the video and only output rows whose source frame
+// lies in [t0, t1) are written (the others belong to other ranks); the single-GPU call passes 0, 0, INT_MAX.
 __global__ void __launch_bounds__(256)
 dpselect_gather_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ idx, uint4* __restrict__ out,
-                       int N, int nvec, long long rows, int sync) {
+                       int N, int nvec, long long rows, int sync, int frame_first, int t0, int t1) {
     const int lane = threadIdx.x & 31;
     const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long GW = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -409,7 +413,8 @@ dpselect_gather_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ 
         const long long j = r / N;
         const int p = (int)(r - j * N);
         const int src_t = sync ? idx[j] : idx[r];
-        const uint4* src = x + ((size_t)src_t * N + p) * (size_t)nvec;
+        if (src_t < t0 || src_t >= t1) continue;
+        const uint4* src = x + ((size_t)(src_t - frame_first) * N + p) * (size_t)nvec;
         uint4* dst = out + (size_t)r * nvec;
         int v = lane;
         for (; v + 7 * 32 < nvec; v += 8 * 32) {
@@ -523,13 +528,8 @@ extern "C" int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t 
     if (C % 8 != 0) return RTK_E_UNSUPPORTED;
     if ((((uintptr_t)x | (uintptr_t)out) & 15u) != 0) return RTK_E_ALIGN;
     if (t > T) return RTK_E_BADARG;
-    if (t == T) {
-        // idx is strictly ascending per column (rtk_dpselect_select): keeping every frame is the identity, and the
-        // compaction is one device-to-device copy at copy-engine speed (the shipped recipe, compression_ratio 1.0)
-        cudaError_t e = cudaMemcpyAsync(out, x, (size_t)T * N * C * 2, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
-        ++::rtk::g_launches;
-        return e == cudaSuccess ? 0 : (int)e;
-    }
+    // (t == T, the shipped compression_ratio 1.0, is the identity: the same kernel copies it - no copy-engine shortcut,
+    //  so that the operator's bandwidth figure is this library's own)
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -537,7 +537,26 @@ extern "C" int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t 
     long long grid = (rows + 7) / 8;
     if (grid > (long long)sms * 8) grid = (long long)sms * 8;
     dpselect_gather_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
-        (const uint4*)x, idx, (uint4*)out, (int)N, (int)(C / 8), rows, sync);
+        (const uint4*)x, idx, (uint4*)out, (int)N, (int)(C / 8), rows, sync, 0, 0, INT_MAX);
+    RTK_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int rtk_dpselect_gather_owned(const void* x_local, int64_t frames_local, int64_t frame_first, int64_t t0, int64_t t1,
+                                         int64_t N, int64_t C, const int32_t* idx, int64_t t, int sync, void* out, void* stream) {
+    RTK_NVTX("rtk_dpselect_gather_owned");
+    if (!x_local || !idx || !out || frames_local < 1 || N < 1 || C < 1 || t < 1) return RTK_E_BADARG;
+    if (t0 < frame_first || t1 > frame_first + frames_local || t0 > t1) return RTK_E_BADARG;
+    if (C % 8 != 0) return RTK_E_UNSUPPORTED;
+    if ((((uintptr_t)x_local | (uintptr_t)out) & 15u) != 0) return RTK_E_ALIGN;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long rows = (long long)t * N;
+    long long grid = (rows + 7) / 8;
+    if (grid > (long long)sms * 8) grid = (long long)sms * 8;
+    dpselect_gather_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x_local, idx, (uint4*)out, (int)N, (int)(C / 8), rows, sync, (int)frame_first, (int)t0, (int)t1);
     RTK_CHECK_LAUNCH();
     return 0;
 }

@@ -384,18 +384,107 @@ __device__ __forceinline__ void pivot_select_body(const __nv_bfloat16* __restric
     }
 }
 
+// ---- peer exchange of the per-KV-head score rows (KV-head split of one video): NVLink P2P stores from a
+//      one-CTA kernel, a release store of the epoch into a flag word on every rank, an acquire spin in the select kernel
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+struct XchgPut {
+    const __nv_bfloat16* src;        // this rank's rows inside its own buffer
+    __nv_bfloat16* dst[8];           // the same rows inside every rank's buffer (dst[rank] == src: skipped)
+    uint32_t* flags[8];              // flags[r] + rank is written with the epoch
+    long long n;                     // bf16 elements
+    int world, rank;
+    uint32_t epoch;
+};
+__global__ void __launch_bounds__(1024)
+pivot_xchg_put_kernel(XchgPut p) {
+    pdl_enter();
+    for (int r = 0; r < p.world; ++r) {
+        if (r == p.rank) continue;
+        __nv_bfloat16* dst = p.dst[r];
+        if ((((uintptr_t)p.src | (uintptr_t)dst) & 15u) == 0) {
+            const long long nv = p.n >> 3;
+            for (long long i = threadIdx.x; i < nv; i += blockDim.x)
+                reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(p.src)[i];
+            for (long long i = (nv << 3) + threadIdx.x; i < p.n; i += blockDim.x) dst[i] = p.src[i];
+        } else {
+            for (long long i = threadIdx.x; i < p.n; i += blockDim.x) dst[i] = p.src[i];
+        }
+    }
+    __threadfence_system();          // every thread's peer stores are performed before ...
+    __syncthreads();
+    if ((int)threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank, p.epoch);      // ... the flags go up
+}
+
+// the same for all layers of a chunk: one CTA per layer moves that layer's rows, a one-CTA kernel behind it raises the flags
+struct XchgPutBatch {
+    const __nv_bfloat16* src[kMaxBatchLayers];
+    __nv_bfloat16* dst[kMaxBatchLayers][8];
+    long long n;                     // bf16 elements per layer
+    int world, rank;
+};
+__global__ void __launch_bounds__(1024)
+pivot_xchg_put_batch_kernel(const __grid_constant__ XchgPutBatch p) {
+    pdl_enter();
+    const int layer = blockIdx.x;
+    const __nv_bfloat16* src = p.src[layer];
+    for (int r = 0; r < p.world; ++r) {
+        if (r == p.rank) continue;
+        __nv_bfloat16* dst = p.dst[layer][r];
+        if ((((uintptr_t)src | (uintptr_t)dst) & 15u) == 0) {
+            const long long nv = p.n >> 3;
+            for (long long i = threadIdx.x; i < nv; i += blockDim.x)
+                reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+            for (long long i = (nv << 3) + threadIdx.x; i < p.n; i += blockDim.x) dst[i] = src[i];
+        } else {
+            for (long long i = threadIdx.x; i < p.n; i += blockDim.x) dst[i] = src[i];
+        }
+    }
+    __threadfence_system();
+}
+struct XchgFlags {
+    uint32_t* flags[8];
+    int world, rank;
+    uint32_t epoch;
+};
+__global__ void __launch_bounds__(32)
+pivot_xchg_flag_kernel(XchgFlags p) {
+    pdl_enter();                     // every CTA of the put kernel has completed (and fenced its peer stores)
+    __threadfence_system();
+    if ((int)threadIdx.x < p.world) st_release_sys(p.flags[threadIdx.x] + p.rank, p.epoch);
+}
+
 __global__ void __launch_bounds__(kSelThreads)
 pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int L, const uint8_t* __restrict__ keymask,
                     int keep, int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ score_out,
-                    const long long* __restrict__ tpos, long long* __restrict__ tmin_out) {
+                    const long long* __restrict__ tpos, long long* __restrict__ tmin_out,
+                    const uint32_t* __restrict__ wait_flags, int wait_n, uint32_t wait_epoch) {
     pdl_enter();
+    if (wait_flags) {
+        // rows of the other ranks arrive over NVLink: nothing of head_scores is read before every rank's flag is up
+        if ((int)threadIdx.x < wait_n)
+            while (ld_acquire_sys(wait_flags + threadIdx.x) != wait_epoch) __nanosleep(64);
+        __syncthreads();
+    }
     pivot_select_body(head_scores, KVH, L, keymask, keep, keep_idx, score_out, tpos, tmin_out);
 }
 
 // one CTA per layer of the chunk
 __global__ void __launch_bounds__(kSelThreads)
-pivot_select_batch_kernel(const __grid_constant__ BatchLayers t, int KVH, int L, int keep, int reforge, long long* __restrict__ tmin) {
+pivot_select_batch_kernel(const __grid_constant__ BatchLayers t, int KVH, int L, int keep, int reforge, long long* __restrict__ tmin,
+                          const uint32_t* __restrict__ wait_flags, int wait_n, uint32_t wait_epoch) {
     pdl_enter();
+    if (wait_flags) {
+        if ((int)threadIdx.x < wait_n)
+            while (ld_acquire_sys(wait_flags + threadIdx.x) != wait_epoch) __nanosleep(64);
+        __syncthreads();
+    }
     const int layer = blockIdx.x;
     pivot_select_body(t.head_scores[layer], KVH, L, t.keymask[layer], keep, t.keep_idx[layer], nullptr,
                       reforge ? t.pos[layer] : nullptr, reforge ? tmin + layer : nullptr);
@@ -642,7 +731,8 @@ extern "C" int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L,
     cudaError_t e = cudaFuncSetAttribute(pivot_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream, (const __nv_bfloat16*)head_scores, (int)KVH,
-                   (int)L, keymask, (int)keep, keep_idx, (__nv_bfloat16*)score_out, (const long long*)nullptr, (long long*)nullptr);
+                   (int)L, keymask, (int)keep, keep_idx, (__nv_bfloat16*)score_out, (const long long*)nullptr, (long long*)nullptr,
+                   (const uint32_t*)nullptr, 0, 0u);
     return 0;
 }
 
@@ -761,6 +851,15 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
     int64_t qsh = a->q_stride_h, qsl = a->q_stride_l, ksh = a->k_stride_h, ksl = a->k_stride_l;
     int rc;
     const bool fused_tables = a->reforge && a->inv_freq;
+    const bool xchg = a->xchg_world > 1;
+    if (a->skip_score && a->skip_select) return RTK_E_BADARG;
+    if (xchg) {
+        if (a->xchg_world > 8 || a->xchg_rank < 0 || a->xchg_rank >= a->xchg_world || !(a->skip_select || a->skip_score))
+            return RTK_E_BADARG;
+        for (int r = 0; r < a->xchg_world; ++r)
+            if (!a->xchg_scores[r] || !a->xchg_flags[r]) return RTK_E_BADARG;
+    }
+    const int64_t score_rows = a->score_rows > 0 ? a->score_rows : KVH;
     if (a->reforge) {
         if (!a->pos || !a->pos_out) return RTK_E_BADARG;
         const void *c = a->cos, *s = a->sin;
@@ -781,30 +880,53 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
                 p.bound[i] = acc;
             }
             if (sec && acc != D) return RTK_E_UNSUPPORTED;
-            RTK_LAUNCH_PDL(pivot_unrope_qk_kernel, (unsigned)((L + kUnropeTok - 1) / kUnropeTok), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)q,
-                           (const long long*)a->pos, a->inv_freq, a->attention_scaling, (__nv_bfloat16*)qu, p);
+            // (skip_score: the copies of the preceding skip_select call are still in the workspace)
+            if (!a->skip_score)
+                RTK_LAUNCH_PDL(pivot_unrope_qk_kernel, (unsigned)((L + kUnropeTok - 1) / kUnropeTok), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)q,
+                               (const long long*)a->pos, a->inv_freq, a->attention_scaling, (__nv_bfloat16*)qu, p);
         } else {
             if (!c || !s) return RTK_E_BADARG;
-            rc = rope_qk_reverse(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, c, s, n_pos_tab, sec, a->inv_scale2, qu, ku,
-                                 (cudaStream_t)stream);
-            if (rc) return rc;
+            if (!a->skip_score) {
+                rc = rope_qk_reverse(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, c, s, n_pos_tab, sec, a->inv_scale2, qu, ku,
+                                     (cudaStream_t)stream);
+                if (rc) return rc;
+            }
         }
         q = qu; k = ku; qsh = ksh = L * D; qsl = ksl = D;
     }
-    if (a->ev_score_begin) cudaEventRecord((cudaEvent_t)a->ev_score_begin, (cudaStream_t)stream);
-    rc = rtk_pivot_score(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, a->head_scores, score_ws, rtk_pivot_score_workspace_bytes(H, L), stream);
-    if (rc) return rc;
-    if (a->ev_score_end) cudaEventRecord((cudaEvent_t)a->ev_score_end, (cudaStream_t)stream);
-    if (a->skip_select) return 0;
+    if (!a->skip_score) {
+        if (a->ev_score_begin) cudaEventRecord((cudaEvent_t)a->ev_score_begin, (cudaStream_t)stream);
+        rc = rtk_pivot_score(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, a->head_scores, score_ws, rtk_pivot_score_workspace_bytes(H, L), stream);
+        if (rc) return rc;
+        if (a->ev_score_end) cudaEventRecord((cudaEvent_t)a->ev_score_end, (cudaStream_t)stream);
+    }
+    if (a->skip_select) {
+        if (xchg) {
+            // this rank's rows go into every peer's buffer, then the flags go up: one CTA, NVLink stores
+            XchgPut xp = {};
+            xp.src = (const __nv_bfloat16*)a->head_scores;
+            xp.n = (long long)KVH * L;
+            xp.world = a->xchg_world; xp.rank = a->xchg_rank; xp.epoch = a->xchg_epoch;
+            if (xp.src != (const __nv_bfloat16*)a->xchg_scores[a->xchg_rank] + (size_t)a->xchg_rank * KVH * L) return RTK_E_BADARG;
+            for (int r = 0; r < a->xchg_world; ++r) {
+                xp.dst[r] = (__nv_bfloat16*)a->xchg_scores[r] + (size_t)a->xchg_rank * KVH * L;
+                xp.flags[r] = a->xchg_flags[r];
+            }
+            RTK_LAUNCH_PDL(pivot_xchg_put_kernel, 1, 1024, 0, (cudaStream_t)stream, xp);
+        }
+        return 0;
+    }
     {
         if (a->keep < 1 || a->keep > L) return RTK_E_BADARG;
         if (L > 16384) return RTK_E_UNSUPPORTED;
         const size_t smem = (size_t)L * 4 + 112 * 4;
         cudaError_t e = cudaFuncSetAttribute(pivot_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
+        if (xchg && a->head_scores != a->xchg_scores[a->xchg_rank]) return RTK_E_BADARG;
         RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream, (const __nv_bfloat16*)a->head_scores,
-                       (int)KVH, (int)L, a->keymask, (int)a->keep, a->keep_idx, (__nv_bfloat16*)nullptr,
-                       (const long long*)(a->reforge ? a->pos : nullptr), a->reforge ? tmin : (long long*)nullptr);
+                       (int)score_rows, (int)L, a->keymask, (int)a->keep, a->keep_idx, (__nv_bfloat16*)nullptr,
+                       (const long long*)(a->reforge ? a->pos : nullptr), a->reforge ? tmin : (long long*)nullptr,
+                       (const uint32_t*)(xchg ? a->xchg_flags[a->xchg_rank] : nullptr), xchg ? a->xchg_world : 0, a->xchg_epoch);
     }
     // K (possibly the un-rotated copy), V (caller's strides), positions and - on the fast path - the forward rotation
     // at the re-indexed positions: one launch, one CTA per kept token
@@ -896,21 +1018,47 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
         acc += (a0.n_pos == 3) ? a0.mrope_section[i % 3] : 0;
         rp.bound[i] = acc;
     }
+    const bool xchg = a0.xchg_world > 1;
+    const int64_t score_rows = a0.score_rows > 0 ? a0.score_rows : KVH;
     if (reforge) {
         if (a0.n_pos == 3 && acc != D) return RTK_E_UNSUPPORTED;
-        RTK_LAUNCH_PDL(pivot_unrope_qk_batch_kernel, dim3((unsigned)((L + kUnropeTok - 1) / kUnropeTok), (unsigned)n), 256, 0, st, t, a0.inv_freq,
-                       a0.attention_scaling, rp);
+        // (skip_score: the un-rotated copies of the preceding skip_select call are still in the workspace)
+        if (!a0.skip_score)
+            RTK_LAUNCH_PDL(pivot_unrope_qk_batch_kernel, dim3((unsigned)((L + kUnropeTok - 1) / kUnropeTok), (unsigned)n), 256, 0, st, t, a0.inv_freq,
+                           a0.attention_scaling, rp);
     }
-    if (a0.ev_score_begin) cudaEventRecord((cudaEvent_t)a0.ev_score_begin, st);
-    int rc = pivot_score_batch(sb, score_ws, rtk_pivot_score_workspace_bytes(H * n, L), st);
-    if (rc) return rc;
-    if (a0.ev_score_end) cudaEventRecord((cudaEvent_t)a0.ev_score_end, st);
+    if (!a0.skip_score) {
+        if (a0.ev_score_begin) cudaEventRecord((cudaEvent_t)a0.ev_score_begin, st);
+        int rc = pivot_score_batch(sb, score_ws, rtk_pivot_score_workspace_bytes(H * n, L), st);
+        if (rc) return rc;
+        if (a0.ev_score_end) cudaEventRecord((cudaEvent_t)a0.ev_score_end, st);
+    }
+    if (a0.skip_select) {
+        if (xchg) {
+            // every layer's rows into every peer's buffer (one CTA per layer), then the flags of the batch
+            XchgPutBatch xp = {};
+            xp.n = (long long)KVH * L; xp.world = a0.xchg_world; xp.rank = a0.xchg_rank;
+            for (int i = 0; i < n; ++i) {
+                xp.src[i] = (const __nv_bfloat16*)a[i].head_scores;
+                if (xp.src[i] != (const __nv_bfloat16*)a[i].xchg_scores[a0.xchg_rank] + (size_t)a0.xchg_rank * KVH * L) return RTK_E_BADARG;
+                for (int r = 0; r < a0.xchg_world; ++r)
+                    xp.dst[i][r] = (__nv_bfloat16*)a[i].xchg_scores[r] + (size_t)a0.xchg_rank * KVH * L;
+            }
+            RTK_LAUNCH_PDL(pivot_xchg_put_batch_kernel, (unsigned)n, 1024, 0, st, xp);
+            XchgFlags xf = {};
+            xf.world = a0.xchg_world; xf.rank = a0.xchg_rank; xf.epoch = a0.xchg_epoch;
+            for (int r = 0; r < a0.xchg_world; ++r) xf.flags[r] = a0.xchg_flags[r];
+            RTK_LAUNCH_PDL(pivot_xchg_flag_kernel, 1, 32, 0, st, xf);
+        }
+        return 0;
+    }
     {
         const size_t smem = (size_t)L * 4 + 112 * 4;
         cudaError_t e = cudaFuncSetAttribute(pivot_select_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        RTK_LAUNCH_PDL(pivot_select_batch_kernel, (unsigned)n, kSelThreads, smem, st, t, (int)KVH, (int)L, (int)a0.keep,
-                       reforge ? 1 : 0, tmin);
+        RTK_LAUNCH_PDL(pivot_select_batch_kernel, (unsigned)n, kSelThreads, smem, st, t, (int)score_rows, (int)L, (int)a0.keep,
+                       reforge ? 1 : 0, tmin, (const uint32_t*)(xchg ? a0.xchg_flags[a0.xchg_rank] : nullptr),
+                       xchg ? a0.xchg_world : 0, a0.xchg_epoch);
     }
     {
         CompactParams p = {};
@@ -931,7 +1079,13 @@ extern "C" int rtk_pivot_update_batch(const rtk_pivot_update_args* layers, int64
     if (!layers || n_layers < 1 || !workspace) return RTK_E_BADARG;
     const rtk_pivot_update_args& a0 = layers[0];
     if (a0.H < 1 || a0.KVH < 1 || a0.L < 1 || a0.keep < 1 || a0.keep > a0.L) return RTK_E_BADARG;
-    if (a0.L > 16384 || a0.D % 16 != 0 || a0.D > 256 || a0.skip_select) return RTK_E_UNSUPPORTED;
+    if (a0.L > 16384 || a0.D % 16 != 0 || a0.D > 256) return RTK_E_UNSUPPORTED;
+    if (a0.skip_select && a0.skip_score) return RTK_E_BADARG;
+    if (a0.xchg_world > 1) {
+        // one flag set per call: the exchange covers one group of layers
+        if (n_layers > kMaxBatchLayers) return RTK_E_UNSUPPORTED;
+        if (a0.xchg_world > 8 || a0.xchg_rank < 0 || a0.xchg_rank >= a0.xchg_world || !(a0.skip_select || a0.skip_score)) return RTK_E_BADARG;
+    }
     if (a0.reforge && !a0.inv_freq) return RTK_E_UNSUPPORTED;        // opaque rotary callables go through rtk_pivot_update
     if (((uintptr_t)workspace & 255u) != 0) return RTK_E_ALIGN;
     if (workspace_bytes < rtk_pivot_update_batch_workspace_bytes(a0.H, a0.KVH, a0.L, a0.D, n_layers)) return RTK_E_WORKSPACE;
@@ -940,11 +1094,17 @@ extern "C" int rtk_pivot_update_batch(const rtk_pivot_update_args* layers, int64
         if (!x.q || !x.k || !x.v || !x.k_out || !x.v_out || !x.keep_idx || !x.head_scores) return RTK_E_BADARG;
         if (x.H != a0.H || x.KVH != a0.KVH || x.L != a0.L || x.D != a0.D || x.keep != a0.keep || x.reforge != a0.reforge ||
             x.n_pos != a0.n_pos || x.inv_freq != a0.inv_freq || x.attention_scaling != a0.attention_scaling ||
-            x.inv_scale2 != a0.inv_scale2 || x.skip_select || (x.pos == nullptr) != (a0.pos == nullptr))
+            x.inv_scale2 != a0.inv_scale2 || x.skip_select != a0.skip_select || x.skip_score != a0.skip_score ||
+            x.score_rows != a0.score_rows || x.xchg_world != a0.xchg_world || x.xchg_rank != a0.xchg_rank ||
+            x.xchg_epoch != a0.xchg_epoch || (x.pos == nullptr) != (a0.pos == nullptr))
             return RTK_E_UNSUPPORTED;                                 // one chunk: the layers share shape and rotary
         for (int j = 0; j < 3; ++j)
             if (x.mrope_section[j] != a0.mrope_section[j]) return RTK_E_UNSUPPORTED;
         if (x.reforge && (!x.pos || !x.pos_out)) return RTK_E_BADARG;
+        if (a0.xchg_world > 1)
+            for (int r = 0; r < a0.xchg_world; ++r)
+                if (!x.xchg_scores[r] || !a0.xchg_flags[r]) return RTK_E_BADARG;
+        if (a0.xchg_world > 1 && a0.skip_score && x.head_scores != x.xchg_scores[a0.xchg_rank]) return RTK_E_BADARG;
         if (x.pos && (!x.pos_out || x.n_pos < 1 || x.n_pos > 3)) return RTK_E_BADARG;
         if ((((uintptr_t)x.q | (uintptr_t)x.k | (uintptr_t)x.v | (uintptr_t)x.k_out | (uintptr_t)x.v_out) & 15u) != 0) return RTK_E_ALIGN;
         if ((x.q_stride_h | x.q_stride_l | x.k_stride_h | x.k_stride_l | x.v_stride_h | x.v_stride_l | x.out_stride_h) % 8 != 0)

@@ -105,20 +105,251 @@ def assemble_compacted(rows: torch.Tensor, slots: torch.Tensor, t: int, n_patche
     return out.reshape(1, t, n_patches, rows.shape[1])
 
 
+# ----------------------------------------------------------------------------- DPSelect shard, sync-free form
+_GATHER_BUF = {}
+
+
+def _gather_buffer(dev, n, dtype, tag):
+    key = (dev, dtype, tag)
+    buf = _GATHER_BUF.get(key)
+    if buf is None or buf.numel() < n:
+        buf = _GATHER_BUF[key] = torch.empty(n, dtype=dtype, device=dev)
+    return buf[:n]
+
+
+def dpselect_frame_sharded_fused(x_local: torch.Tensor, t0: int, t1: int, T: int, tgt_mem_len: int, sync: bool = False,
+                                 group=None, out: Optional[torch.Tensor] = None, zero_fill: bool = False):
+    """The frame-range split as four device operations and NO host synchronisation: local distances
+    (``rtk_dpselect_dis(halo)``), ONE ``all_gather_into_tensor`` of the ``[T, N]`` fp32 distances into a preallocated
+    buffer, the replicated selection, and ``rtk_dpselect_gather_owned``, which writes this rank's surviving rows straight
+    into their slots of the reference's ``[1, t, N, C]`` layout.
+
+    Returns ``(out, mask, idx)``: ``out`` (``[1, t, N, C]``, the caller's buffer or a fresh one) has only the slots whose
+    source frame lies in ``[t0, t1)`` written - the rest is left as it was (zeros with ``zero_fill``); mask and indices are
+    identical on every rank.  ``assemble_owned`` sums zero-filled partial outputs when one rank needs the whole tensor."""
+    from . import _native as N_
+    from . import visual_compression as vc
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    halo = t0 > 0
+    assert x_local.shape[0] == (t1 - t0) + int(halo)
+    n_patches, C = x_local.shape[1], x_local.shape[2]
+    ranges = split_range(T, world)
+    assert ranges[rank] == (t0, t1), "frame ranges must come from split_range(T, world)"
+    dis_local = vc.dpselect_distance(x_local, halo=halo)                       # [t1 - t0, N]
+    mx = max(b - a for a, b in ranges)
+    dev = x_local.device
+    if all(b - a == mx for a, b in ranges):
+        dis = _gather_buffer(dev, T * n_patches, torch.float32, "dis").view(T, n_patches)
+        dist.all_gather_into_tensor(dis, dis_local, group=group)
+    else:
+        # ragged split: equal-sized padded blocks through the same single collective, then one compaction copy
+        padded = _gather_buffer(dev, world * mx * n_patches, torch.float32, "dis_pad").view(world, mx, n_patches)
+        mine = _gather_buffer(dev, mx * n_patches, torch.float32, "dis_mine").view(mx, n_patches)
+        mine[: t1 - t0].copy_(dis_local)
+        dist.all_gather_into_tensor(padded, mine, group=group)
+        dis = torch.cat([padded[r, : b - a] for r, (a, b) in enumerate(ranges)], dim=0)
+    idx, mask = vc.dpselect_select(dis, tgt_mem_len, sync)
+    if out is None:
+        alloc = torch.zeros if zero_fill else torch.empty
+        out = alloc((1, tgt_mem_len, n_patches, C), dtype=x_local.dtype, device=dev)
+    xl = x_local.contiguous()
+    with torch.cuda.device(dev):
+        N_.check(N_.lib().rtk_dpselect_gather_owned(xl.data_ptr(), xl.shape[0], t0 - int(halo), t0, t1, n_patches, C,
+                                                    idx.data_ptr(), tgt_mem_len, int(sync), out.data_ptr(),
+                                                    N_.stream_ptr(dev)), "rtk_dpselect_gather_owned")
+    return out, mask, idx
+
+
+def assemble_owned(out_partial: torch.Tensor, group=None) -> torch.Tensor:
+    """every slot is filled on exactly one rank and zero elsewhere: a sum of the bit patterns rebuilds the whole tensor"""
+    bits = out_partial.contiguous().view(torch.int32).clone()      # (NCCL has no 16-bit integer sum; C is even)
+    dist.all_reduce(bits, op=dist.ReduceOp.SUM, group=group)
+    return bits.view(out_partial.dtype)
+
+
 # ---------------------------------------------------------------------------------------------- PivotKV shard
 def gather_head_scores(head_scores_local: torch.Tensor, kv_heads_per_rank: List[int], group=None) -> torch.Tensor:
     """``[KVH_local, L]`` -> ``[KVH, L]`` in global KV-head order (rank r owns a contiguous block of heads)"""
     return all_gather_rows(head_scores_local, kv_heads_per_rank, group)
 
 
+class ScoreExchange:
+    """Where the per-KV-head score rows of every rank meet (one per process group and device).
+
+    ``p2p``: two ``[rows, L]`` bf16 buffers and two sets of flag words in torch symmetric memory, mapped into every rank's
+    address space; the library's one-CTA put kernel stores a rank's rows into all peers over NVLink and raises a flag, the
+    select kernel of every rank waits for all flags (``rtk_pivot_update_args.xchg_*``) - no collective launch at all.
+    ``nccl``: the same two calls around ONE ``all_gather_into_tensor`` on a preallocated buffer (used when symmetric memory
+    is not available, or when asked for with RTK_SHARD_TRANSPORT=nccl)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, group, device, rows: int, L: int, transport: Optional[str] = None):
+        import os
+        transport = transport or os.environ.get("RTK_SHARD_TRANSPORT", "p2p")
+        key = (id(group) if group is not None else 0, device, transport)
+        ex = cls._cache.get(key)
+        if ex is None or ex.capacity < rows * L:
+            ex = cls._cache[key] = cls(group, device, max(rows * L, 8 * 16384), transport)
+        return ex
+
+    def __init__(self, group, device, capacity: int, transport: str):
+        self.group, self.device, self.capacity = group, device, capacity
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.epoch = 0
+        self.transport = transport
+        self.handles = None
+        if transport == "p2p":
+            try:
+                import torch.distributed._symmetric_memory as sm
+                g = group if group is not None else dist.group.WORLD
+                self.scores = sm.empty((2, capacity), dtype=torch.bfloat16, device=device)
+                self.flags = sm.empty((2, 8), dtype=torch.int32, device=device)
+                self.flags.zero_()
+                hs, hf = sm.rendezvous(self.scores, g), sm.rendezvous(self.flags, g)
+                self.score_ptrs = [int(p) for p in hs.buffer_ptrs]
+                self.flag_ptrs = [int(p) for p in hf.buffer_ptrs]
+                self.handles = (hs, hf)
+                torch.cuda.synchronize(device)
+                dist.barrier(group)                       # nobody raises a flag before everybody has cleared theirs
+            except Exception as e:  # noqa: BLE001 - symmetric memory is optional: NCCL carries the same rows
+                import warnings
+                warnings.warn(f"symmetric memory unavailable ({e!r}); the KV-head split uses NCCL all_gather_into_tensor")
+                self.transport = "nccl"
+        if self.transport != "p2p":
+            self.scores = torch.empty((2, capacity), dtype=torch.bfloat16, device=device)
+
+    def begin(self):
+        """next exchange: (parity, epoch)"""
+        self.epoch += 1
+        return self.epoch & 1, self.epoch
+
+    def own_ptr(self, parity: int) -> int:
+        return self.scores.data_ptr() + parity * self.capacity * 2
+
+
 def pivot_update_kv_sharded(query_local, key_local, value_local, keep_len: int, kv_heads_per_rank: List[int],
                             keymask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
-                            rotary_emb=None, mrope_section=None, reforge: bool = False, group=None):
+                            rotary_emb=None, mrope_section=None, reforge: bool = False, group=None,
+                            transport: Optional[str] = None):
     """One compressing update with the KV heads of the chunk split across ranks.
 
     ``query_local [1, G * KVH_local, L, D]`` are the query heads of this rank's KV groups.  Returns
     ``(kept_k [1, KVH_local, keep, D], kept_v, kept_positions, keep_idx, head_scores [KVH, L])``; ``keep_idx`` is
-    identical on every rank."""
+    identical on every rank.
+
+    Two C-ABI calls around one exchange of the ``[KVH_local, L]`` score rows (``rtk_pivot_update`` with ``skip_select``,
+    then with ``skip_score``): un-rotate + score + put | wait + select + compact + re-rotate, eight launches, the rows
+    travelling as NVLink peer stores issued by the library's own kernel (``ScoreExchange``), or as one NCCL
+    ``all_gather_into_tensor``.  Ranks with different numbers of heads take the unfused chain below."""
+    if len(set(kv_heads_per_rank)) != 1 or query_local.dtype != torch.bfloat16:
+        return _pivot_update_kv_sharded_unfused(query_local, key_local, value_local, keep_len, kv_heads_per_rank, keymask,
+                                                position_ids, rotary_emb, mrope_section, reforge, group)
+    import ctypes as C
+
+    from . import _native as N_
+    from . import longvideo_cache as lc
+    dev = query_local.device
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    kvh_local = key_local.shape[1]
+    rows, L = kvh_local * world, query_local.shape[2]
+    ex = ScoreExchange.get(group, dev, rows, L, transport)
+    parity, epoch = ex.begin()
+    a, outs, keepalive, fast, _ = lc.fill_update_args(keymask, reforge, lc._inv_freq_on_device, query_local, key_local, value_local,
+                                                      position_ids, rotary_emb, mrope_section, keep_len)
+    lib = N_.lib()
+    ws = lc._workspace(dev, int(lib.rtk_pivot_update_workspace_bytes(a.H, a.KVH, a.L, a.D)) + 256)
+    ws_ptr = (ws.data_ptr() + 255) & ~255
+    a.workspace, a.workspace_bytes = ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr())
+    own = ex.own_ptr(parity)
+    hs_all = ex.scores[parity, : rows * L].view(rows, L)
+    a.head_scores = own + rank * kvh_local * L * 2
+    a.skip_select, a.skip_score, a.score_rows = 1, 0, rows
+    if ex.transport == "p2p":
+        a.xchg_world, a.xchg_rank, a.xchg_epoch = world, rank, epoch
+        for r in range(world):
+            a.xchg_scores[r] = ex.score_ptrs[r] + parity * ex.capacity * 2
+            a.xchg_flags[r] = ex.flag_ptrs[r] + parity * 8 * 4
+    with torch.cuda.device(dev):
+        N_.check(lib.rtk_pivot_update(C.byref(a), N_.stream_ptr(dev)), "rtk_pivot_update(skip_select)")
+        if ex.transport != "p2p":
+            dist.all_gather_into_tensor(hs_all, hs_all[rank * kvh_local:(rank + 1) * kvh_local], group=group)
+        a.skip_select, a.skip_score = 0, 1
+        a.head_scores = own
+        N_.check(lib.rtk_pivot_update(C.byref(a), N_.stream_ptr(dev)), "rtk_pivot_update(skip_score)")
+    kept_k, kept_v, kept_pos = outs["k_out"], outs["v_out"], outs["pos_out"]
+    if reforge and not fast:
+        cos2, sin2 = rotary_emb(kept_v, kept_pos)
+        lc.pivot_rope(kept_k, cos2, sin2, mrope_section, 1.0, forward=True, out=kept_k)
+    del keepalive
+    return kept_k, kept_v, kept_pos, outs["keep_idx"], hs_all
+
+
+def pivot_update_batch_kv_sharded(layers, keep_len: int, kv_heads_per_rank: List[int], rotary_emb=None, mrope_section=None,
+                                  reforge: bool = False, group=None, transport: Optional[str] = None):
+    """The KV-head split for ALL layers of a chunk at once (deferred compression, SURVEY.md 8(f2) + 8(e)): two
+    ``rtk_pivot_update_batch`` calls around ONE exchange of every layer's ``[KVH_local, L]`` score rows.
+
+    ``layers``: list of ``(query_local, key_local, value_local, keymask or None, position_ids or None)`` with equal shapes.
+    Returns a list of ``(kept_k, kept_v, kept_positions, keep_idx)`` per layer; ``keep_idx`` is identical on every rank.
+    Needs equal heads per rank and a rotary module with a static ``inv_freq`` when ``reforge`` (the batched kernels'
+    envelope); at most 32 layers per call."""
+    import ctypes as C
+
+    from . import _native as N_
+    from . import longvideo_cache as lc
+    assert len(set(kv_heads_per_rank)) == 1 and 1 <= len(layers) <= 32
+    dev = layers[0][0].device
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    kvh_local, L = layers[0][1].shape[1], layers[0][0].shape[2]
+    rows, n = kvh_local * world, len(layers)
+    ex = ScoreExchange.get(group, dev, rows * n, L, transport)
+    parity, epoch = ex.begin()
+    arr = (lc._UpdateArgs * n)()
+    outs_all, keep = [], []
+    for i, (ql, kl, vl, km, pos) in enumerate(layers):
+        a, outs, keepalive, fast, _ = lc.fill_update_args(km, reforge, lc._inv_freq_on_device, ql, kl, vl, pos, rotary_emb,
+                                                          mrope_section, keep_len)
+        if reforge and not fast:
+            raise ValueError("the batched split needs a rotary module with a static inv_freq")
+        base = parity * ex.capacity * 2 + i * rows * L * 2
+        a.head_scores = ex.scores.data_ptr() + base + rank * kvh_local * L * 2
+        a.skip_select, a.skip_score, a.score_rows = 1, 0, rows
+        if ex.transport == "p2p":
+            a.xchg_world, a.xchg_rank, a.xchg_epoch = world, rank, epoch
+            for r in range(world):
+                a.xchg_scores[r] = ex.score_ptrs[r] + base
+                a.xchg_flags[r] = ex.flag_ptrs[r] + parity * 8 * 4
+        arr[i] = a
+        outs_all.append(outs)
+        keep.append(keepalive)
+    lib = N_.lib()
+    a0 = arr[0]
+    ws = lc._workspace(dev, int(lib.rtk_pivot_update_batch_workspace_bytes(a0.H, a0.KVH, a0.L, a0.D, n)) + 256)
+    ws_ptr = (ws.data_ptr() + 255) & ~255
+    ws_bytes = ws.numel() - (ws_ptr - ws.data_ptr())
+    with torch.cuda.device(dev):
+        N_.check(lib.rtk_pivot_update_batch(arr, n, ws_ptr, ws_bytes, N_.stream_ptr(dev)), "rtk_pivot_update_batch(skip_select)")
+        if ex.transport != "p2p":
+            blk = ex.scores[parity, : n * rows * L].view(n, rows, L)
+            with dist._coalescing_manager(group=group, device=dev, async_ops=False):
+                for i in range(n):
+                    dist.all_gather_into_tensor(blk[i], blk[i, rank * kvh_local:(rank + 1) * kvh_local], group=group)
+        for i in range(n):
+            arr[i].skip_select, arr[i].skip_score = 0, 1
+            arr[i].head_scores = ex.scores.data_ptr() + parity * ex.capacity * 2 + i * rows * L * 2
+        N_.check(lib.rtk_pivot_update_batch(arr, n, ws_ptr, ws_bytes, N_.stream_ptr(dev)), "rtk_pivot_update_batch(skip_score)")
+    del keep
+    return [(o["k_out"], o["v_out"], o["pos_out"], o["keep_idx"]) for o in outs_all]
+
+
+def _pivot_update_kv_sharded_unfused(query_local, key_local, value_local, keep_len: int, kv_heads_per_rank: List[int],
+                                     keymask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None,
+                                     rotary_emb=None, mrope_section=None, reforge: bool = False, group=None):
+    """the same update as a chain of the unfused entry points (any split of the heads over the ranks)"""
     from . import longvideo_cache as lc
     q, k = query_local, key_local
     if reforge:

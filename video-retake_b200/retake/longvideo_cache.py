@@ -35,7 +35,7 @@ from . import _native as N
 
 logger = logging.get_logger(__name__)
 
-__all__ = ["PivotKVCache", "build_kvcache", "repeat_kv", "rotate_half", "apply_multimodal_rotary_pos_emb",
+__all__ = ["pivot_update", "PivotKVCache", "build_kvcache", "repeat_kv", "rotate_half", "apply_multimodal_rotary_pos_emb",
            "apply_rotary_pos_emb", "pivot_head_scores", "pivot_select", "pivot_compact", "pivot_rope", "pivot_rope_tables"]
 
 
@@ -210,7 +210,10 @@ class _UpdateArgs(C.Structure):
                 ("pos_out", C.c_void_p), ("keep_idx", C.c_void_p), ("head_scores", C.c_void_p),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("ev_score_begin", C.c_void_p), ("ev_score_end", C.c_void_p),
-                ("pos_out_stride", C.c_int64)]
+                ("pos_out_stride", C.c_int64),
+                ("skip_score", C.c_int32), ("score_rows", C.c_int32),
+                ("xchg_world", C.c_int32), ("xchg_rank", C.c_int32), ("xchg_epoch", C.c_uint32),
+                ("xchg_scores", C.c_void_p * 8), ("xchg_flags", C.c_void_p * 8)]
 
 
 _STATIC_INV_FREQ_ROPE = ("default", "yarn", "linear", "llama3")
@@ -269,6 +272,113 @@ def apply_multimodal_rotary_pos_emb(q, k, cos, sin, mrope_section, unsqueeze_dim
 def apply_rotary_pos_emb(q, k, cos, sin, position_ids=None, unsqueeze_dim=1, reverse=False, attention_scaling=1):
     """1-D rotary twin of the above (``longvideo_cache.py:86-116``; ``cos`` / ``sin`` ``[1, L, D]``)."""
     return _rope_pair(q, k, cos, sin, None, unsqueeze_dim, reverse, attention_scaling)
+
+
+def fill_update_args(keymask, reforge, inv_freq_on, query_states, key_states, value_states, position_ids, rotary_emb_fn,
+                 mrope_section, keep_len, k_out=None, v_out=None, pos_out=None, own_pos=False):
+    """fill one ``rtk_pivot_update_args``; returns (args, outputs, tensors that must outlive the launches, fast)
+    ``k_out`` / ``v_out`` ``[1, KVH, keep, D]`` (rows D apart, any head stride) and ``pos_out`` ``[..., keep]`` default to
+    fresh tensors; ``fast`` is False when the rotary module is opaque (tables come from calling it)"""
+    q, H, L, D, qsh, qsl = _hld(query_states, "query_states")
+    k, KVH, Lk, Dk, ksh, ksl = _hld(key_states, "key_states")
+    v, _, _, _, vsh, vsl = _hld(value_states, "value_states")
+    if Lk != L or Dk != D:
+        raise ValueError("PivotKV scores the chunk's own keys: key and query lengths must match")
+    dev = q.device
+    if k_out is None:
+        k_out = torch.empty((1, KVH, keep_len, D), dtype=torch.bfloat16, device=dev)
+        v_out = torch.empty_like(k_out)
+    head_scores = torch.empty((KVH, L), dtype=torch.bfloat16, device=dev)
+    keep_idx = torch.empty((keep_len,), dtype=torch.int32, device=dev)
+    a = _UpdateArgs()
+    a.q, a.H, a.q_stride_h, a.q_stride_l = q.data_ptr(), H, qsh, qsl
+    a.k, a.KVH, a.k_stride_h, a.k_stride_l = k.data_ptr(), KVH, ksh, ksl
+    a.v, a.v_stride_h, a.v_stride_l = v.data_ptr(), vsh, vsl
+    a.k_stride_h_in, a.k_stride_l_in = ksh, ksl
+    a.L, a.D, a.keep = L, D, keep_len
+    if keymask is not None:
+        N.require_cuda(keymask, "keypatches_mask_chunk", torch.bool)
+        keymask = keymask.contiguous()
+        if keymask.numel() != L:
+            raise ValueError("keypatches_mask_chunk must have one entry per chunk token")
+        a.keymask = keymask.data_ptr()
+    reforge = bool(reforge)
+    a.reforge = int(reforge)
+    pos_flat = cos = sin = inv = None
+    if position_ids is not None:
+        N.require_cuda(position_ids, "position_ids", torch.int64)
+        # own_pos (deferred launches): the ids are read at after_forward(), by which time the caller may have
+        # re-based the SAME tensor in place for the next layers (the attention forward does) - keep a private copy
+        pos_flat = position_ids.reshape(-1, L).clone() if own_pos else position_ids.reshape(-1, L).contiguous()
+        a.n_pos, a.pos = pos_flat.shape[0], pos_flat.data_ptr()
+        if pos_out is None:
+            pos_out = torch.empty(position_ids.shape[:-1] + (keep_len,), dtype=torch.int64, device=dev)
+        a.pos_out = pos_out.data_ptr()
+        a.pos_out_stride = pos_out.stride(0) if pos_flat.shape[0] > 1 else keep_len
+        if mrope_section and pos_flat.shape[0] == 3:
+            a.mrope_section = (C.c_int32 * 3)(*[int(s) for s in mrope_section])
+    fast = True
+    if reforge:
+        scaling = float(rotary_emb_fn.attention_scaling)
+        a.attention_scaling, a.inv_scale2 = scaling, _inv_scale2(scaling)
+        static = _rotary_inv_freq(rotary_emb_fn)
+        if static is not None:
+            inv = inv_freq_on(static[0], dev)
+            a.inv_freq = inv.data_ptr()
+        else:
+            fast = False
+            cos, sin = rotary_emb_fn(value_states, position_ids)
+            cos, sin = cos.contiguous(), sin.contiguous()
+            if cos.dtype != torch.bfloat16 or cos.numel() != pos_flat.shape[0] * L * D:
+                raise ValueError("rotary_emb must return bf16 [n_pos, 1, L, D] tables")
+            a.cos, a.sin = cos.data_ptr(), sin.data_ptr()
+    a.k_out, a.v_out, a.out_stride_h = k_out.data_ptr(), v_out.data_ptr(), k_out.stride(1)
+    a.keep_idx, a.head_scores = keep_idx.data_ptr(), head_scores.data_ptr()
+    sig = (H, KVH, L, D, keep_len, reforge, int(a.n_pos), a.inv_freq, float(a.attention_scaling), tuple(a.mrope_section),
+           dev.index)
+    outs = {"k_out": k_out, "v_out": v_out, "pos_out": pos_out, "head_scores": head_scores, "keep_idx": keep_idx}
+    keepalive = (q, k, v, keymask, pos_flat, cos, sin, inv)
+    return a, outs, keepalive, fast, sig
+
+
+_INV_FREQ_DEV = {}
+
+
+def _inv_freq_on_device(inv_freq: torch.Tensor, dev) -> torch.Tensor:
+    """fp32 copy of a rotary module's inv_freq on ``dev`` (cached per tensor)"""
+    if inv_freq.device == dev and inv_freq.dtype == torch.float32 and inv_freq.is_contiguous():
+        return inv_freq
+    key = (id(inv_freq), dev)
+    hit = _INV_FREQ_DEV.get(key)
+    if hit is None or hit[1] is not inv_freq:
+        hit = _INV_FREQ_DEV[key] = (inv_freq.to(device=dev, dtype=torch.float32).contiguous(), inv_freq)
+    return hit[0]
+
+
+def pivot_update(query_states: torch.Tensor, key_states: torch.Tensor, value_states: torch.Tensor, keep_len: int,
+                 keymask: Optional[torch.Tensor] = None, position_ids: Optional[torch.Tensor] = None, rotary_emb=None,
+                 mrope_section=None, reforge: bool = False, score_events=None):
+    """The compressing part of ``PivotKVCache.update`` (``longvideo_cache.py:244-306``) as ONE C-ABI call, without the cache
+    bookkeeping: un-rotate, score, select, compact, re-index, re-rotate.
+    -> (kept K ``[1, KVH, keep, D]``, kept V, kept positions or None, kept indices int32 ``[keep]``, head scores ``[KVH, L]``)"""
+    a, outs, keepalive, fast, _ = fill_update_args(keymask, reforge, _inv_freq_on_device, query_states, key_states,
+                                                   value_states, position_ids, rotary_emb, mrope_section, keep_len)
+    dev = query_states.device
+    lib = N.lib()
+    ws = _workspace(dev, int(lib.rtk_pivot_update_workspace_bytes(a.H, a.KVH, a.L, a.D)) + 256)
+    ws_ptr = (ws.data_ptr() + 255) & ~255
+    a.workspace, a.workspace_bytes = ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr())
+    if score_events is not None:
+        a.ev_score_begin, a.ev_score_end = score_events
+    with torch.cuda.device(dev):
+        N.check(lib.rtk_pivot_update(C.byref(a), N.stream_ptr(dev)), "rtk_pivot_update")
+    k_out, v_out, pos_out = outs["k_out"], outs["v_out"], outs["pos_out"]
+    if reforge and not fast:
+        # opaque rotary callable: ask it for the tables of the re-indexed positions, then re-rotate in place
+        cos2, sin2 = rotary_emb(v_out, pos_out)
+        pivot_rope(k_out, cos2, sin2, mrope_section, 1.0, forward=True, out=k_out)
+    del keepalive
+    return k_out, v_out, pos_out, outs["keep_idx"], outs["head_scores"]
 
 
 class PivotKVLayer(DynamicLayer):
@@ -575,102 +685,22 @@ class PivotKVCache(DynamicCache):
     # ------------------------------------------------------------------------------------------------ update
     def _update_args(self, query_states, key_states, value_states, position_ids, rotary_emb_fn, mrope_section, keep_len,
                      k_out=None, v_out=None, pos_out=None, own_pos=False):
-        """fill one ``rtk_pivot_update_args``; returns (args, outputs, tensors that must outlive the launches, fast)
-        ``k_out`` / ``v_out`` ``[1, KVH, keep, D]`` (rows D apart, any head stride) and ``pos_out`` ``[..., keep]`` default to
-        fresh tensors; ``fast`` is False when the rotary module is opaque (tables come from calling it)"""
-        q, H, L, D, qsh, qsl = _hld(query_states, "query_states")
-        k, KVH, Lk, Dk, ksh, ksl = _hld(key_states, "key_states")
-        v, _, _, _, vsh, vsl = _hld(value_states, "value_states")
-        if Lk != L or Dk != D:
-            raise ValueError("PivotKV scores the chunk's own keys: key and query lengths must match")
-        dev = q.device
-        if k_out is None:
-            k_out = torch.empty((1, KVH, keep_len, D), dtype=torch.bfloat16, device=dev)
-            v_out = torch.empty_like(k_out)
-        head_scores = torch.empty((KVH, L), dtype=torch.bfloat16, device=dev)
-        keep_idx = torch.empty((keep_len,), dtype=torch.int32, device=dev)
-        a = _UpdateArgs()
-        a.q, a.H, a.q_stride_h, a.q_stride_l = q.data_ptr(), H, qsh, qsl
-        a.k, a.KVH, a.k_stride_h, a.k_stride_l = k.data_ptr(), KVH, ksh, ksl
-        a.v, a.v_stride_h, a.v_stride_l = v.data_ptr(), vsh, vsl
-        a.k_stride_h_in, a.k_stride_l_in = ksh, ksl
-        a.L, a.D, a.keep = L, D, keep_len
-        keymask = getattr(self, "keypatches_mask_chunk", None)
-        if keymask is not None:
-            N.require_cuda(keymask, "keypatches_mask_chunk", torch.bool)
-            keymask = keymask.contiguous()
-            if keymask.numel() != L:
-                raise ValueError("keypatches_mask_chunk must have one entry per chunk token")
-            a.keymask = keymask.data_ptr()
-        reforge = bool(self.pos_embed_reforge)
-        a.reforge = int(reforge)
-        pos_flat = cos = sin = inv = None
-        if position_ids is not None:
-            N.require_cuda(position_ids, "position_ids", torch.int64)
-            # own_pos (deferred launches): the ids are read at after_forward(), by which time the caller may have
-            # re-based the SAME tensor in place for the next layers (the attention forward does) - keep a private copy
-            pos_flat = position_ids.reshape(-1, L).clone() if own_pos else position_ids.reshape(-1, L).contiguous()
-            a.n_pos, a.pos = pos_flat.shape[0], pos_flat.data_ptr()
-            if pos_out is None:
-                pos_out = torch.empty(position_ids.shape[:-1] + (keep_len,), dtype=torch.int64, device=dev)
-            a.pos_out = pos_out.data_ptr()
-            a.pos_out_stride = pos_out.stride(0) if pos_flat.shape[0] > 1 else keep_len
-            if mrope_section and pos_flat.shape[0] == 3:
-                a.mrope_section = (C.c_int32 * 3)(*[int(s) for s in mrope_section])
-        fast = True
-        if reforge:
-            scaling = float(rotary_emb_fn.attention_scaling)
-            a.attention_scaling, a.inv_scale2 = scaling, _inv_scale2(scaling)
-            static = _rotary_inv_freq(rotary_emb_fn)
-            if static is not None:
-                inv = self._inv_freq_on(static[0], dev)
-                a.inv_freq = inv.data_ptr()
-            else:
-                fast = False
-                cos, sin = rotary_emb_fn(value_states, position_ids)
-                cos, sin = cos.contiguous(), sin.contiguous()
-                if cos.dtype != torch.bfloat16 or cos.numel() != pos_flat.shape[0] * L * D:
-                    raise ValueError("rotary_emb must return bf16 [n_pos, 1, L, D] tables")
-                a.cos, a.sin = cos.data_ptr(), sin.data_ptr()
-        a.k_out, a.v_out, a.out_stride_h = k_out.data_ptr(), v_out.data_ptr(), k_out.stride(1)
-        a.keep_idx, a.head_scores = keep_idx.data_ptr(), head_scores.data_ptr()
-        sig = (H, KVH, L, D, keep_len, reforge, int(a.n_pos), a.inv_freq, float(a.attention_scaling), tuple(a.mrope_section),
-               dev.index)
-        outs = {"k_out": k_out, "v_out": v_out, "pos_out": pos_out, "head_scores": head_scores, "keep_idx": keep_idx}
-        keepalive = (q, k, v, keymask, pos_flat, cos, sin, inv)
-        return a, outs, keepalive, fast, sig
+        return fill_update_args(getattr(self, "keypatches_mask_chunk", None), self.pos_embed_reforge, self._inv_freq_on,
+                                query_states, key_states, value_states, position_ids, rotary_emb_fn, mrope_section, keep_len,
+                                k_out, v_out, pos_out, own_pos)
 
     def _inv_freq_on(self, inv_freq: torch.Tensor, dev) -> torch.Tensor:
         """fp32 copy of the rotary module's inv_freq on ``dev`` (the module's own tensor when it already is one)"""
-        if inv_freq.device == dev and inv_freq.dtype == torch.float32 and inv_freq.is_contiguous():
-            return inv_freq
-        key = (id(inv_freq), dev)
-        hit = getattr(self, "_inv_cache", None)
-        if hit is None or hit[0] != key:
-            self._inv_cache = (key, inv_freq.to(device=dev, dtype=torch.float32).contiguous(), inv_freq)
-        return self._inv_cache[1]
+        return _inv_freq_on_device(inv_freq, dev)
 
     def _compress_chunk(self, query_states, key_states, value_states, position_ids, rotary_emb_fn, mrope_section,
                         keep_len):
         """one ``rtk_pivot_update`` call -> (kept K [1,KVH,keep,D], kept V, kept positions or None)"""
-        a, outs, keepalive, fast, _ = self._update_args(query_states, key_states, value_states, position_ids, rotary_emb_fn,
-                                                        mrope_section, keep_len)
-        dev = query_states.device
-        lib = N.lib()
-        ws = _workspace(dev, int(lib.rtk_pivot_update_workspace_bytes(a.H, a.KVH, a.L, a.D)) + 256)
-        ws_ptr = (ws.data_ptr() + 255) & ~255
-        a.workspace, a.workspace_bytes = ws_ptr, ws.numel() - (ws_ptr - ws.data_ptr())
-        if self.score_events is not None:
-            a.ev_score_begin, a.ev_score_end = self.score_events
-            self.score_events = None
-        with torch.cuda.device(dev):
-            N.check(lib.rtk_pivot_update(C.byref(a), N.stream_ptr(dev)), "rtk_pivot_update")
-        k_out, v_out, pos_out = outs["k_out"], outs["v_out"], outs["pos_out"]
-        if self.pos_embed_reforge and not fast:
-            # opaque rotary callable: ask it for the tables of the re-indexed positions, then re-rotate in place
-            cos2, sin2 = rotary_emb_fn(v_out, pos_out)
-            pivot_rope(k_out, cos2, sin2, mrope_section, 1.0, forward=True, out=k_out)
-        self.last_head_scores, self.last_keep_indices = outs["head_scores"], outs["keep_idx"]
+        ev, self.score_events = self.score_events, None
+        k_out, v_out, pos_out, keep_idx, head_scores = pivot_update(
+            query_states, key_states, value_states, keep_len, getattr(self, "keypatches_mask_chunk", None), position_ids,
+            rotary_emb_fn, mrope_section, self.pos_embed_reforge, ev)
+        self.last_head_scores, self.last_keep_indices = head_scores, keep_idx
         return k_out, v_out, pos_out
 
     def _defer_chunk(self, layer, layer_idx, query_states, key_states, value_states, position_ids, rotary_emb_fn,
