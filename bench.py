@@ -602,15 +602,26 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    for _ in range(a.warmup):
-        run_step(s, x, q, k, v, rotary, lc, vc, pos_grid)
-    sync_all()
-    parity = None
+    # kept-index parity self-check and the r_v = 0.5 DPSelect figure: BEFORE the warm-up, so that the warm-up steps leave
+    # the caching allocator in the state the timed steps find
+    parity = dps_half = None
     if rank == 0 and not a.no_parity:
         _, kp_mask = vc.memory_bank_compress_keyframe(x[None], s.t, 3, sync=False)
         parity = parity_record(s, q, k, v, rotary, lc, pos_grid, kp_mask)
         del kp_mask
+        th = max(1, s.T // 2)
+        for _ in range(2):
+            vc.memory_bank_compress_keyframe(x[None], th, 3, sync=False)
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        for _ in range(5):
+            vc.memory_bank_compress_keyframe(x[None], th, 3, sync=False)
+        h1.record()
+        torch.cuda.synchronize()
+        dps_half = (h0.elapsed_time(h1) / 5, 2.0 * s.T * s.N * s.C + 4.0 * s.T * s.N + 4.0 * th * s.N * s.C)
         torch.cuda.empty_cache()
+    for _ in range(a.warmup):
+        run_step(s, x, q, k, v, rotary, lc, vc, pos_grid)
     sync_all()
     sampler = clocks_sampler(local_rank) if rank == 0 else None
     launches0 = _native.launch_count()
@@ -749,7 +760,8 @@ def main():
     dps_ms = sum(a.elapsed_time(b) for a, b in timer.dpselect) / max(1, len(timer.dpselect))
     hbm = peaks.get("hbm_gbs", 6650.0)
     dps_bytes = 2.0 * s.T * s.N * s.C + 4.0 * s.T * s.N + 4.0 * s.t * s.N * s.C
-    dpselect_roofline = {"kernels": "dpselect_dis + dpselect_select_patch + dpselect_gather (one operator call)", "bound": "hbm",
+    dpselect_roofline = {"kernels": "dpselect_dis + dpselect_select_patch + dpselect_gather: one rtk_dpselect_keyframe call, all three "
+                                    "this library's own kernels (r_v = 1 is an identity gather through the same kernel)", "bound": "hbm",
                          "achieved": dps_bytes / (dps_ms * 1e-3) / 1e9 if dps_ms > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                          "frac": (dps_bytes / (dps_ms * 1e-3) / 1e9 / hbm) if dps_ms > 0 else 0.0, "ms_per_call": dps_ms,
                          "algorithmic_bytes": dps_bytes}
@@ -760,6 +772,11 @@ def main():
             "gpu_launches": int(launches),
             "step_ms": {"median": sorted(per_step)[len(per_step) // 2], "min": min(per_step), "max": max(per_step)}}
     line["build_id"] = _native.build_id()
+    if dps_half is not None:
+        hms, hby = dps_half
+        line["roofline_dpselect_rv0.5"] = {"bound": "hbm", "achieved": hby / (hms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                                           "frac": hby / (hms * 1e-3) / 1e9 / hbm, "ms_per_call": hms, "algorithmic_bytes": hby,
+                                           "what": f"the same operator at t = T/2 = {max(1, s.T // 2)} (five back-to-back calls before the timed region)"}
     if parity is not None:
         line["parity"] = parity
     if sharded is not None:

@@ -81,6 +81,11 @@ int rtk_dpselect_select(const float* dis, int64_t T, int64_t N, int64_t t, int s
 int rtk_dpselect_gather(const void* x, int64_t T, int64_t N, int64_t C, const int32_t* idx, int64_t t,
                         int sync, void* out, void* stream);
 
+/* memory_bank_compress_keyframe (visual_compression.py:86-177) as ONE call: rtk_dpselect_dis + _select + _gather launched
+ * back to back.  dis (fp32 [T, N]), idx (int32 [t, N] or [t]), mask ([t * N]) and out (bf16 [t, N, C]) are the caller's. */
+int rtk_dpselect_keyframe(const void* x, int64_t T, int64_t N, int64_t C, int64_t t, int sync, float* dis,
+                          int32_t* idx, uint8_t* mask, void* out, void* stream);
+
 /* Frame-range split of ONE video over the GPUs of a box: the compaction of visual_compression.py:138 / :173
  * restricted to the frames a rank owns.  x_local holds frames [frame_first, frame_first + frames_local) of the video (bf16
  * [frames_local, N, C]); idx is the replicated result of rtk_dpselect_select on the all-gathered distances; only the rows of

@@ -12,7 +12,8 @@ libs = sorted(glob.glob(os.path.join(ROOT, "build", "ab", "librtk_*.so")))
 res = {}
 outs = {}
 p, i64, sz = C.c_void_p, C.c_int64, C.c_size_t
-for rnd in range(3):
+NCALLS = int(os.environ.get("NCALLS", "50"))
+for rnd in range(int(os.environ.get("ROUNDS", "3"))):
     for path in libs:
         lib = C.CDLL(path)
         fn = lib.rtk_pivot_score
@@ -26,11 +27,11 @@ for rnd in range(3):
         outs[os.path.basename(path)] = hs.clone()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(50):
+        for _ in range(NCALLS):
             call()
         b.record()
         torch.cuda.synchronize()
-        res.setdefault(os.path.basename(path), []).append(a.elapsed_time(b) / 50)
+        res.setdefault(os.path.basename(path), []).append(a.elapsed_time(b) / NCALLS)
 print(json.dumps(res, indent=1))
 ref = outs[sorted(outs)[0]]
 print({n: int((o.view(torch.int16) != ref.view(torch.int16)).sum()) for n, o in outs.items()}, 'mismatches vs first variant')

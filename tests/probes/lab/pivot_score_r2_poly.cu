@@ -18,11 +18,12 @@
 // four softmax groups of four warps (one warp per TMEM lane quarter): groups 0, 1 serve the accumulators of the first
 // stationary tile, groups 2, 3 those of the second, each taking 64 of the 128 columns with one tcgen05.ld.32x32b.x64.
 // Per logit the softmax side issues two in-place fp32->bf16 roundings (F2FP with a zero low half), packed f32x2
-// scale / FMA / add, one MUFU.EX2 and (pass 1) half an FMNMX3.
+// scale / FMA / add, one exp2 and (pass 1) half an FMNMX3.  exp2 is MUFU.EX2, except for RTK_SCORE_POLY_P1 / _P2 of
+// every 16 logit pairs, which take a degree-5 polynomial on the FMA pipe (same accuracy class, see ex2_poly2): the
+// MUFU pipe (16 results per clock and SM) is the busiest unit of the kernel.
 // This file holds the shipped configuration only; the A/B variants of round 1 (ring depths, 16/32-column TMEM loads,
 // more softmax groups, lazy rescale ...) live in tests/probes/lab/pivot_score_r1_variants.cu with their results in
-// profiles/r1_score_ab_experiments.md, and round 2's FMA-pipe polynomial exp2 (no gain under sustained load) in
-// tests/probes/lab/pivot_score_r2_poly.cu / profiles/r2_score_experiments.md.
+// profiles/r1_score_ab_experiments.md.
 #include <cuda.h>
 
 #include "rtk_common.cuh"
@@ -40,6 +41,13 @@ constexpr int kAccBufs = 4;           // 128-column TMEM buffers
 constexpr int kStatSlots = kStages + kAccBufs;
 constexpr uint32_t kTileBytes = kTile * kHeadDim * 2;        // 32 KiB
 constexpr uint32_t kHalfBytes = kTile * 64 * 2;              // one [128][64] swizzle-128B box
+
+#ifndef RTK_SCORE_POLY_P1
+#define RTK_SCORE_POLY_P1 0           // pass 1: logit pairs out of every 16 whose exp2 runs on the FMA pipe
+#endif
+#ifndef RTK_SCORE_POLY_P2
+#define RTK_SCORE_POLY_P2 0           // pass 2: the same
+#endif
 
 struct ScoreSmem {
     // offsets inside dynamic shared memory (1024-byte aligned base)
@@ -196,11 +204,42 @@ __device__ __forceinline__ uint64_t logit_chain2(uint32_t r0, uint32_t r1, uint6
 }
 __device__ __forceinline__ float logit_chain1(float acc, float inv) { return round_bf16(round_bf16(acc) * inv); }
 
-// exp2 of a packed pair: two MUFU.EX2
+// exp2 of a packed pair: two MUFU.EX2 ...
 __device__ __forceinline__ uint64_t ex2_mufu2(uint64_t x2) {
     float x0, x1;
     upk2(x2, x0, x1);
     return pk2(ex2f(x0), ex2f(x1));
+}
+// ... or, to take load off the MUFU pipe, on the FMA pipe: x = n + f with n = rint(x), f in [-0.5, 0.5]; 2^f by a
+// degree-5 minimax polynomial (relative error 2.3e-7 evaluated in fp32 = 2^-22.1, the class of ex2.approx: 2^-22.5),
+// 2^n spliced into the exponent field.  Inputs below -125 (masked columns: -inf) give 2^-125 instead of 0, which no
+// fp32 sum next to a term >= 2^-24 can see.
+__device__ __forceinline__ uint64_t ex2_poly2(uint64_t x2) {
+    float x0, x1;
+    upk2(x2, x0, x1);
+    x2 = pk2(fmaxf(x0, -125.f), fmaxf(x1, -125.f));
+    const float magic = 12582912.f;                              // 1.5 * 2^23: t = magic + rint(x) exactly
+    const uint64_t t2 = add2(x2, pk2(magic, magic));
+    const uint64_t f2 = add2(x2, fma2(t2, pk2(-1.f, -1.f), pk2(magic, magic)));      // x - (t - magic)
+    uint64_t p2 = pk2(0.0013280266430228949f, 0.0013280266430228949f);
+    p2 = fma2(p2, f2, pk2(0.009676850400865078f, 0.009676850400865078f));
+    p2 = fma2(p2, f2, pk2(0.055507123470306396f, 0.055507123470306396f));
+    p2 = fma2(p2, f2, pk2(0.24022091925144196f, 0.24022091925144196f));
+    p2 = fma2(p2, f2, pk2(0.6931469440460205f, 0.6931469440460205f));
+    p2 = fma2(p2, f2, pk2(1.0000001192092896f, 1.0000001192092896f));
+    float t0, t1, p0, p1;
+    upk2(t2, t0, t1);
+    upk2(p2, p0, p1);
+    // magic's bit pattern ends in 22 zeros, so (bits(t) << 23) = rint(x) * 2^23 (mod 2^32): add it to the exponent field
+    return pk2(__uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23)),
+               __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23)));
+}
+// pair j of a 64-column block (j = 0..31): which unit evaluates its exp2
+template <int POLY>
+__device__ __forceinline__ uint64_t ex2_pair(uint64_t x2, int j) {
+    // spread the polynomial pairs evenly over each group of 16: pair j takes it when floor(j*POLY/16) steps up
+    if (POLY > 0 && ((j % 16) * POLY) / 16 != (((j % 16) + 1) * POLY) / 16) return ex2_poly2(x2);
+    return ex2_mufu2(x2);
 }
 
 struct SoftmaxState {
@@ -234,16 +273,16 @@ __device__ __forceinline__ void softmax_cols(uint32_t (&r)[64], int valid, Softm
         const uint64_t nmm = pk2(-mm, -mm);
 #pragma unroll
         for (int i = 0; i < NC; i += 4) {
-            st.acc = add2(st.acc, ex2_mufu2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm)));
-            st.acc = add2(st.acc, ex2_mufu2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, nmm)));
+            st.acc = add2(st.acc, ex2_pair<RTK_SCORE_POLY_P1>(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, nmm), i / 2));
+            st.acc = add2(st.acc, ex2_pair<RTK_SCORE_POLY_P1>(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, nmm), i / 2 + 1));
         }
     } else {
 #pragma unroll
         for (int i = 0; i < NC; i += 4) {
             const float4 cc = *reinterpret_cast<const float4*>(cq + i);
             float e0, e1, e2, e3;
-            upk2(ex2_mufu2(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y))), e0, e1);
-            upk2(ex2_mufu2(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w))), e2, e3);
+            upk2(ex2_pair<RTK_SCORE_POLY_P2>(fma2(logit_chain2(r[i], r[i + 1], inv2), l2e2, pk2(-cc.x, -cc.y)), i / 2), e0, e1);
+            upk2(ex2_pair<RTK_SCORE_POLY_P2>(fma2(logit_chain2(r[i + 2], r[i + 3], inv2), l2e2, pk2(-cc.z, -cc.w)), i / 2 + 1), e2, e3);
             add_bf16_pair(st.c0, st.c1, pack_bf16x2_rn(e0, e1));
             add_bf16_pair(st.c0, st.c1, pack_bf16x2_rn(e2, e3));
         }

@@ -57,6 +57,15 @@ def _worker(rank, world, port, sync):
         out = rd.assemble_compacted(rows, slots, t, N)
         want_out, want_mask = od.memory_bank_compress_keyframe(x[None], t, 3, sync=sync)
         assert torch.equal(out, want_out)
+        # the sync-free form writes owned rows straight into their slots of a zero-filled [1, t, N, C] buffer: the sum of the
+        # ranks' bit patterns is the whole tensor (what rtk_dpselect_gather_owned + assemble_owned do on the GPU)
+        full_idx = idx if idx.dim() == 2 else idx[:, None].expand(-1, N)
+        own = (full_idx >= t0) & (full_idx < t1)
+        part = torch.zeros(1, t, N, C, dtype=torch.bfloat16)
+        xb = x.to(torch.bfloat16)
+        want_b = xb.gather(0, full_idx[:, :, None].expand(-1, -1, C))
+        part[0][own] = want_b[own]
+        assert torch.equal(rd.assemble_owned(part), want_b[None])
         # every slot is owned exactly once
         cnt = torch.zeros(t * N, dtype=torch.int64)
         cnt[slots] += 1

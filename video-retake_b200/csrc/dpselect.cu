@@ -561,6 +561,17 @@ extern "C" int rtk_dpselect_gather_owned(const void* x_local, int64_t frames_loc
     return 0;
 }
 
+// the whole operator in one call: one crossing of the FFI, three back-to-back launches
+extern "C" int rtk_dpselect_keyframe(const void* x, int64_t T, int64_t N, int64_t C, int64_t t, int sync, float* dis,
+                                     int32_t* idx, uint8_t* mask, void* out, void* stream) {
+    RTK_NVTX("rtk_dpselect_keyframe");
+    int rc = rtk_dpselect_dis(x, T, N, C, 0, dis, stream);
+    if (rc) return rc;
+    rc = rtk_dpselect_select(dis, T, N, t, sync, idx, mask, stream);
+    if (rc) return rc;
+    return rtk_dpselect_gather(x, T, N, C, idx, t, sync, out, stream);
+}
+
 extern "C" int rtk_gather_rows(const void* x, int64_t row_bytes, const int64_t* src_row, int64_t rows, void* out,
                                void* stream) {
     RTK_NVTX("rtk_gather_rows");

@@ -41,6 +41,7 @@ def lib() -> C.CDLL:
         "rtk_dpselect_select": ([p, i64, i64, i64, i32, p, p, p], C.c_int),
         "rtk_dpselect_gather": ([p, i64, i64, i64, p, i64, i32, p, p], C.c_int),
         "rtk_gather_rows": ([p, i64, p, i64, p, p], C.c_int),
+        "rtk_dpselect_keyframe": ([p, i64, i64, i64, i64, i32, p, p, p, p, p], C.c_int),
         "rtk_dpselect_gather_owned": ([p, i64, i64, i64, i64, i64, i64, p, i64, i32, p, p], C.c_int),
         "rtk_mallm_workspace_bytes": ([i64, i64, i64, i32], sz),
         "rtk_mallm_compress": ([p, p, i64, i64, i64, i64, i32, i32, p, p, p, sz, p], C.c_int),
@@ -96,7 +97,7 @@ def build_id() -> str:
 
 
 EXPORTS = ("rtk_version", "rtk_build_id", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
-           "rtk_dpselect_gather", "rtk_gather_rows", "rtk_dpselect_gather_owned", "rtk_mallm_workspace_bytes", "rtk_mallm_compress", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
+           "rtk_dpselect_gather", "rtk_dpselect_keyframe", "rtk_gather_rows", "rtk_dpselect_gather_owned", "rtk_mallm_workspace_bytes", "rtk_mallm_compress", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
            "rtk_pivot_select", "rtk_pivot_compact", "rtk_pivot_rope_tables", "rtk_pivot_update_workspace_bytes",
            "rtk_pivot_update", "rtk_pivot_update_batch_workspace_bytes", "rtk_pivot_update_batch", "rtk_kv_block_copy")
 

@@ -87,9 +87,17 @@ def memory_bank_compress_keyframe(memory_bank: torch.Tensor, tgt_mem_len: int, w
     if not 1 <= tgt_mem_len <= T:
         raise RuntimeError(f"selected index k out of range (k={tgt_mem_len}, T={T})")     # torch.topk's error
     x = memory_bank[0]
-    dis = dpselect_distance(x)
-    idx, mask = dpselect_select(dis, tgt_mem_len, bool(sync))
-    out = dpselect_gather(x, idx, bool(sync))[None]
+    N.require_cuda(x, "memory_bank", torch.bfloat16)
+    x = x.contiguous()
+    dev = x.device
+    dis = torch.empty((T, Np), dtype=torch.float32, device=dev)
+    idx = torch.empty((tgt_mem_len,) if sync else (tgt_mem_len, Np), dtype=torch.int32, device=dev)
+    mask = torch.empty((tgt_mem_len * Np,), dtype=torch.bool, device=dev)
+    out = torch.empty((1, tgt_mem_len, Np, Cc), dtype=x.dtype, device=dev)
+    with torch.cuda.device(dev):                 # distances, selection and compaction: one C-ABI call, three launches
+        N.check(N.lib().rtk_dpselect_keyframe(x.data_ptr(), T, Np, Cc, tgt_mem_len, int(bool(sync)), dis.data_ptr(),
+                                              idx.data_ptr(), mask.data_ptr(), out.data_ptr(), N.stream_ptr(dev)),
+                "rtk_dpselect_keyframe")
     if return_indices:
         return out, mask, idx.long()
     return out, mask
