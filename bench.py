@@ -163,6 +163,30 @@ def synth_host(s, pool, seed):
     return [x, q, k, v]
 
 
+def synth_device(s, pool, seed, dev):
+    """the same synthetic inputs generated ON the GPU (seconds instead of a minute of host randn for the 3.4 GB LLaVA video),
+    plus pinned host copies for the end-to-end leg: -> ([x, q, k, v] on dev, [x, q, k, v] pinned)"""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    gc = torch.Generator().manual_seed(seed)
+    x = torch.empty(s.T, s.N, s.C, dtype=torch.bfloat16, device=dev)
+    t = 0
+    while t < s.T:                                         # x[t] = scene + 0.3 * noise, scenes of 3..40 grids
+        run = min(int(torch.randint(3, 41, (1,), generator=gc)), s.T - t)
+        scene = torch.randn(s.N, s.C, generator=g, device=dev)
+        x[t:t + run] = (scene[None] + 0.3 * torch.randn(run, s.N, s.C, generator=g, device=dev)).to(torch.bfloat16)
+        t += run
+    q = torch.randn(pool, s.L, s.H, s.D, generator=g, device=dev).to(torch.bfloat16)
+    k = torch.randn(pool, s.L, s.KVH, s.D, generator=g, device=dev).to(torch.bfloat16)
+    v = torch.randn(pool, s.L, s.KVH, s.D, generator=g, device=dev).to(torch.bfloat16)
+    host = []
+    for t_ in (x, q, k, v):
+        h = torch.empty(t_.shape, dtype=t_.dtype, pin_memory=True)
+        h.copy_(t_)
+        host.append(h)
+    torch.cuda.synchronize()
+    return [x, q, k, v], host
+
+
 class ScoreTimer:
     """CUDA-event pairs recorded by the library around a sample of the scoring launches (rtk_pivot_score inside
     rtk_pivot_update) in the timed region; the events live on the stream the kernels are launched on."""
@@ -223,22 +247,25 @@ def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer=None):
                 timer.arm(cache)
             cache.update(k[j:j + 1, :Lc].transpose(1, 2), v[j:j + 1, :Lc].transpose(1, 2), layer,
                          {"query_states": q[j:j + 1, :Lc].transpose(1, 2), "position_ids": pos, "rotary_emb": rotary,
-                          "mrope_section": s.mrope})
+                          "mrope_section": s.mrope, "position_ids_owned": True})      # a per-layer buffer, rewritten next chunk
         if timer is not None and s.deferred:
             timer.arm(cache)
         cache.after_forward()                                # the chunk loop's hook (qwen2_vl.py:715-716)
     return cache.last_keep_indices, cache.get_seq_length(0)
 
 
-def measured_traffic(build_id, s):
-    """profiles/ncu_score_traffic.json: {"build_id", "L", "deferred", "bytes_per_layer", "source"} written by
-    profiles/summarize_ncu.py from an `ncu --set full` capture of the scoring launches"""
+def measured_traffic(s):
+    """profiles/ncu_score_traffic.json: [{"score_source_sha", "L", "deferred", "bytes_per_layer", "source"}] from an
+    `ncu --set full` capture of the scoring launches; used only when the capture was taken from the scoring source in this
+    tree (SHA-256 of csrc/pivot_score.cu) at this shape - never a stale constant"""
+    import hashlib
     try:
         rec = json.load(open(os.path.join(ROOT, "profiles", "ncu_score_traffic.json")))
+        sha = hashlib.sha256(open(os.path.join(ROOT, "video-retake_b200", "csrc", "pivot_score.cu"), "rb").read()).hexdigest()[:16]
     except Exception:
         return None
     for r in rec if isinstance(rec, list) else [rec]:
-        if r.get("build_id") == build_id and r.get("L") == s.L and bool(r.get("deferred")) == bool(s.deferred):
+        if r.get("score_source_sha") == sha and r.get("L") == s.L and bool(r.get("deferred")) == bool(s.deferred):
             return r.get("bytes_per_layer")
     return None
 
@@ -590,8 +617,7 @@ def main():
         return
     timer = ScoreTimer(every=2, calls_per_pair=s.layers) if s.deferred else ScoreTimer()
     rotary = make_rotary(dev, s.name)
-    host = synth_host(s, a.pool, 1234 + rank)
-    x, q, k, v = [h.to(dev, non_blocking=True) for h in host]
+    (x, q, k, v), host = synth_device(s, a.pool, 1234 + rank, dev)
     ar = torch.arange(s.L, device=dev)
     pos_grid = torch.stack([ar // s.N, (ar % s.N) // 16, ar % 16])[:, None] if s.mrope else ar[None]
     torch.cuda.synchronize()
@@ -748,7 +774,7 @@ def main():
                 "ms_per_call": score_ms, "calls_timed": len(timer.pairs),
                 # dram__bytes_read.sum + dram__bytes_write.sum of both launches per layer from the committed `ncu --set full`
                 # capture - used only when that capture was taken from THIS build and shape, else null (never a stale constant)
-                "traffic": measured_traffic(_native.build_id(), s),
+                "traffic": measured_traffic(s),
                 # an exact two-pass softmax needs 2*H*L^2 fp32 ex2; B200 issues 16 MUFU per clock and SM
                 "xu_floor_ms": 2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3,
                 "frac_of_xu_floor": (2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3) / score_ms if score_ms > 0 else 0.0,

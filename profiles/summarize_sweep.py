@@ -1,18 +1,24 @@
-"""gpurun_out/sweep.jsonl (tools_sweep.py) -> markdown table.  python profiles/summarize_sweep.py in.jsonl > out.md"""
+"""gpurun_out/sweep_n*.jsonl (tools_sweep.py) -> markdown table.  python profiles/summarize_sweep.py title in1.jsonl [in2.jsonl ...] > out.md"""
 import json
 import sys
 
-rows = [json.loads(l) for l in open(sys.argv[1]) if l.strip()]
-print("# Round 1 - kernel sweep on one B200 (BASELINE config 5 + LLaVA-Video shape), `python tools_sweep.py`\n")
+title = sys.argv[1]
+rows = []
+for f in sys.argv[2:]:
+    rows += [json.loads(l) for l in open(f) if l.strip()]
+print(f"# {title}\n")
 print("Each point is `bench.py --steps 2 --warmup 3` on that configuration (inputs resident in HBM, deferred compression: one batched")
-print("`rtk_pivot_update_batch` per chunk). `score` = the scoring of one layer (CUDA events around the batched scoring of a chunk inside the")
-print("timed region / 28 layers), frac = algorithmic flops / measured sustained bf16 peak; `dpselect` = the whole operator,")
-print("frac = algorithmic bytes / measured HBM peak (small videos are launch/latency dominated: 3 kernels for <= 0.5 GB).\n")
-print("| shape | frames | r_v | r_kv | frames/s | ms/step | score ms (frac) | dpselect ms (frac) |")
-print("|---|---|---|---|---|---|---|---|")
+print("`rtk_pivot_update_batch` per chunk; N > 1: one video per GPU under torchrun, frames/s is the aggregate). `score` = the scoring of")
+print("one layer (CUDA events around the batched scoring of a chunk inside the timed region / 28 layers), frac = algorithmic flops /")
+print("measured sustained bf16 peak; `dpselect` = the whole operator, frac = algorithmic bytes / measured HBM peak.\n")
+print("| shape | frames | GPUs | r_v | r_kv | frames/s | per GPU | ms/step | score ms (frac) | dpselect ms (frac) | e2e frames/s |")
+print("|---|---|---|---|---|---|---|---|---|---|---|")
 for r in rows:
     if "error" in r:
-        print(f"| {r['shape']} | {r['frames']} | {r['rv']} | {r['rkv']} | error | | | |")
+        print(f"| {r['shape']} | {r['frames']} | {r.get('n_gpus', 1)} | {r['rv']} | {r['rkv']} | error | | | | | |")
         continue
-    print(f"| {r['shape']} | {r['frames']} | {r['visual_ratio']} | {r['kv_ratio']:.3f} | {r['frames_per_s']:.0f} | {r['ms_per_step']:.1f} | "
-          f"{r['score_ms']:.3f} ({r['score_frac']:.3f}) | {r['dpselect_ms']:.3f} ({r['dpselect_frac']:.2f}) |")
+    n = r.get("n_gpus", 1)
+    e2e = r.get("e2e_frames_per_s")
+    print(f"| {r['shape']} | {r['frames']} | {n} | {r['visual_ratio']} | {r['kv_ratio']:.3f} | {r['frames_per_s']:.0f} | {r['frames_per_s'] / n:.0f} | "
+          f"{r['ms_per_step']:.1f} | {r['score_ms']:.3f} ({r['score_frac']:.3f}) | {r['dpselect_ms']:.3f} ({r['dpselect_frac']:.2f}) | "
+          f"{'%.0f' % e2e if e2e else '-'} |")

@@ -43,5 +43,12 @@ for (H, KVH, L, D) in ((4, 2, 130, 64), (28, 4, 200, 128), (8, 8, 1, 128)):
                 cache.update(k, v, layer, {"query_states": q, "position_ids": pos, "rotary_emb": rot, "mrope_section": sec})
             cache.after_forward()
         _ = cache.layers[0].keys.sum().item()
+# round 2: the two-call KV-head split with both ranks emulated on this GPU (put kernel, flags, waiting select), the owned-slot
+# compaction of the frame-range split and the one-call DPSelect operator - the same code as tests/test_gpu_exchange.py
+import test_gpu_exchange as tx
+for L_, reforge_ in ((333, True), (130, False)):
+    tx.test_two_emulated_ranks_equal_single_gpu(L_, reforge_)
+for sync_ in (False, True):
+    tx.test_gather_owned_fills_exactly_the_owned_slots(sync_)
 torch.cuda.synchronize()
 print("sanitize pass done")

@@ -67,7 +67,9 @@ def retake_Qwen2Attention_forward(self, hidden_states, position_embeddings, atte
     if cache is not None:
         if isinstance(cache, PivotKVCache):
             cache_kwargs = {"sin": sin, "cos": cos, "query_states": query_states, "position_ids": position_ids,
-                            "rotary_emb": rotary}
+                            "rotary_emb": rotary,
+                            # with re-forging the ids above are this layer's own copy: the cache may keep them as they are
+                            "position_ids_owned": position_ids is not None and position_ids is not pos}
             key_states, value_states = cache.update(key_states, value_states, self.layer_idx, cache_kwargs)
         else:
             key_states, value_states = cache.update(key_states, value_states, self.layer_idx)

@@ -704,7 +704,7 @@ class PivotKVCache(DynamicCache):
         return k_out, v_out, pos_out
 
     def _defer_chunk(self, layer, layer_idx, query_states, key_states, value_states, position_ids, rotary_emb_fn,
-                     mrope_section, keep_len) -> bool:
+                     mrope_section, keep_len, own_pos=True) -> bool:
         """queue this layer's compression for the batched call; False when it has to run now (opaque rotary module)"""
         if self.pos_embed_reforge and _rotary_inv_freq(rotary_emb_fn) is None:
             return False
@@ -720,7 +720,7 @@ class PivotKVCache(DynamicCache):
             pos_out = self._position_slots(position_ids, keep_len, layer_idx)      # kept positions land in the position cache
         k_dst, v_dst = layer.shrink_tail(q_len, keep_len, self)                    # kept rows land in the cache itself
         a, outs, keepalive, _, sig = self._update_args(query_states, key_states, value_states, position_ids, rotary_emb_fn,
-                                                       mrope_section, keep_len, k_dst, v_dst, pos_out, own_pos=True)
+                                                       mrope_section, keep_len, k_dst, v_dst, pos_out, own_pos=own_pos)
         self._deferred.append({"args": a, "outs": outs, "keepalive": keepalive, "sig": sig, "layer": layer,
                                "device": query_states.device})
         self._last_head_scores, self._last_keep_indices = outs["head_scores"], outs["keep_idx"]
@@ -737,6 +737,9 @@ class PivotKVCache(DynamicCache):
         logger.warning_once("Enable PivotKVCache compression: length after compression %.2f" % (self.compression_ratio))
         cache_kwargs = cache_kwargs if cache_kwargs is not None else {}
         position_ids = cache_kwargs.pop("position_ids", None)
+        # optional (not in the reference): the caller hands this tensor over - it will not be modified before after_forward() -
+        # so that deferred compression need not take a private copy of the ids
+        pos_owned = bool(cache_kwargs.pop("position_ids_owned", False))
 
         # 1) this chunk attends to everything: [past | chunk] is what the caller gets back.  The previous layer's
         #    attention is on the stream by now, so its kept rows may land: both go out as ONE block-copy launch.
@@ -764,7 +767,8 @@ class PivotKVCache(DynamicCache):
             # 2) score the chunk's own keys with the chunk's queries, keep the top ratio * q_len
             keep_len = max(1, int(self.compression_ratio * q_len))
             if self.deferred_compression and self._defer_chunk(layer, layer_idx, query_states, key_states, value_states,
-                                                               position_ids, rotary_emb_fn, mrope_section, keep_len):
+                                                               position_ids, rotary_emb_fn, mrope_section, keep_len,
+                                                               own_pos=not pos_owned):
                 # 2') ... later: all layers of the chunk in one batched call, kept rows written in place (flush_deferred)
                 self.update_num_evicted_tokens(k_len - keep_len, layer_idx)
                 return key_states_output, value_states_output

@@ -57,8 +57,12 @@ def retake_Qwen2VLAttention_forward(self, hidden_states, attention_mask=None, po
     if isinstance(cache, PivotKVCache) and cache.pos_embed_reforge and pos3d is not None and rotary is not None:
         # temporal ids continue after this layer's (compacted) cache; sync-free form of qwen2_vl.py:68-73
         assert bsz == 1
+        # (out of place: every layer gets ITS OWN id tensor, handed over to the cache - deferred compression reads it at
+        #  after_forward() - and the next layer re-bases relative to it, exactly like the reference's in-place update)
         prev = cache.get_prev_temporal_idx(self.layer_idx)
-        pos3d[0, 0, :] += prev + 1 - pos3d[0, 0, 0]
+        shifted = pos3d.clone()
+        shifted[0, 0, :] += prev + 1 - pos3d[0, 0, 0]
+        pos3d = cache.retake_position_ids = shifted
         cos, sin = rotary(value_states, pos3d)
     else:
         cos, sin = position_embeddings
@@ -67,7 +71,8 @@ def retake_Qwen2VLAttention_forward(self, hidden_states, attention_mask=None, po
     if cache is not None:
         if isinstance(cache, PivotKVCache):
             cache_kwargs = {"sin": sin, "cos": cos, "query_states": query_states, "position_ids": pos3d,
-                            "rotary_emb": rotary, "mrope_section": mrope_section}
+                            "rotary_emb": rotary, "mrope_section": mrope_section,
+                            "position_ids_owned": cache.pos_embed_reforge}
             key_states, value_states = cache.update(key_states, value_states, self.layer_idx, cache_kwargs)
         else:
             key_states, value_states = cache.update(key_states, value_states, self.layer_idx)
