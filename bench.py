@@ -394,21 +394,28 @@ def sharded_within_video(dev, dist, rank, world, steps=3):
                      f"{gsz} GPUs per video ({n_groups} video(s) in flight); DPSelect T={T} -> t={t} split by frame range",
            "gpus_per_video": gsz, "videos": n_groups}
     # ---- bit-equality self-check against the single-GPU operators (every rank checks its own heads / frames)
-    sk, sv, sp, sidx, _ = single(0)
-    ok = True
-    for transport in ("p2p", "nccl"):
-        kk, vv, pp, idx, hs = sharded(0, transport)
-        ok = ok and bool(torch.equal(idx, sidx)) and bool(torch.equal(kk, sk[:, g0:g0 + per[0]])) \
-            and bool(torch.equal(vv, sv[:, g0:g0 + per[0]])) and bool(torch.equal(pp, sp))
+    # (the kept set of the split equals the single-GPU one unless a score sits on the cut: a unit split between CTAs folds
+    #  its fp32 partials in another order when the launch holds other heads - then the rule of tests/test_gpu_index_parity.py)
+    from helpers import index_parity
+    ok = cut_ok = True
+    for j in range(pool):
+        sk, sv, sp, sidx, shs = single(j)
+        for transport in ("p2p", "nccl"):
+            kk, vv, pp, idx, hs = sharded(j, transport)
+            same, justified, _ = index_parity(idx, sidx, shs.float().mean(0).to(torch.bfloat16), keep)
+            cut_ok = cut_ok and justified
+            ok = ok and same and bool(torch.equal(kk, sk[:, g0:g0 + per[0]])) and bool(torch.equal(vv, sv[:, g0:g0 + per[0]])) \
+                and bool(torch.equal(pp, sp))
     want_out, want_mask, want_idx = vc.memory_bank_compress_keyframe(x[None], t, 3, sync=False, return_indices=True)
     dps_out = torch.zeros((1, t, N, C), dtype=torch.bfloat16, device=dev)      # the split writes its own slots into it
     part, mask2, idx2 = rd.dpselect_frame_sharded_fused(xl, t0, t1, T, t, False, group, dps_out)
     own = ((idx2.long() >= t0) & (idx2.long() < t1))[None, :, :, None].expand_as(want_out)
     ok = ok and bool(torch.equal(mask2, want_mask)) and bool(torch.equal(idx2.long(), want_idx)) \
         and bool(torch.equal(part[own], want_out[own]))
-    okt = torch.tensor([int(ok)], device=dev)
+    okt = torch.tensor([int(ok), int(cut_ok)], device=dev)
     dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-    out["bit_identical_to_single_gpu"] = bool(int(okt))
+    out["bit_identical_to_single_gpu"] = bool(int(okt[0]))
+    out["kept_indices_differ_only_on_the_cut_if_at_all"] = bool(int(okt[1]))
     del want_out
     # ---- one compressing update (the judge's unit): single GPU, split with NVLink peer stores, split with one NCCL collective
     n = 40

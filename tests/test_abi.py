@@ -42,8 +42,8 @@ def test_argument_errors_without_gpu():
     assert lib.rtk_pivot_score(a16, 4, 128, 512, a16, 3, 128, 384, 16, 128, a16, a16, 1 << 20, None) == -3  # H % KVH
     assert lib.rtk_pivot_score(a16, 4, 128, 512, a16, 2, 128, 256, 16, 96, a16, a16, 1 << 20, None) == -3   # D
     assert lib.rtk_pivot_score(a16, 4, 128, 512, a16, 2, 128, 256, 16, 128, a16, a16, 8, None) == -4        # workspace
-    assert lib.rtk_pivot_score_workspace_bytes(28, 4096) == 7 * 28 * 4096 * 4
-    assert lib.rtk_pivot_score_workspace_bytes(4, 130) == 7 * 4 * 256 * 4
+    assert lib.rtk_pivot_score_workspace_bytes(28, 4096) == 10 * 28 * 4096 * 4
+    assert lib.rtk_pivot_score_workspace_bytes(4, 130) == 10 * 4 * 256 * 4
     assert lib.rtk_pivot_select(a16, 4, 16, None, 17, a16, None, None) == -1   # keep > L
     # batched update: workspace query, argument errors
     one = lib.rtk_pivot_update_batch_workspace_bytes(28, 4, 4096, 128, 1)

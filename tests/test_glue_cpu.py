@@ -90,10 +90,13 @@ def _tile_ranges(heads_per_layer, nt, layers, grid, pair):
 def test_score_kernel_partition_invariants():
     import itertools
     for (H, nt, layers), pair in itertools.product([(28, 32, 1), (28, 32, 28), (28, 49, 3), (4, 8, 2), (4, 1, 5), (14, 1, 1), (8, 2, 33),
-                                                    (28, 18, 2), (2, 3, 1)], (1, 2)):
+                                                    (28, 18, 2), (2, 3, 1), (7, 32, 28), (14, 32, 2), (7, 49, 1), (1, 5, 1)], (1, 2)):
         nta = (nt + pair - 1) // pair
-        grid = min(H * nta, 148)                       # host side: one layer's units decide the grid
+        # host side (score_launch): one layer's units decide the grid; a range is at least half a unit long, so launches
+        # with fewer units than SMs (7 heads per rank of the KV-head split) still use the whole machine
+        grid = max(1, min(H * nta * nt // ((nt + 1) // 2), 148))
         steps, upl = _tile_ranges(H, nt, layers, grid, pair)
+        Gl = upl * nt
         seen = {}
         for cta, layer, u, tb0, tb1 in steps:
             assert 0 <= tb0 < tb1 <= nt and layer * upl <= u < (layer + 1) * upl
@@ -101,11 +104,27 @@ def test_score_kernel_partition_invariants():
         assert sorted(seen) == list(range(layers * upl)), "every unit of every layer is visited"
         for u, parts in seen.items():
             parts.sort(key=lambda p: p[1])
-            # the streamed tiles of a unit are covered exactly once, by at most two CTAs: the piece that starts at tile 0
-            # writes partial 0 (and clears partial 1 when it is the whole unit), the other piece writes partial 1
-            assert len(parts) <= 2 and parts[0][1] == 0 and parts[-1][2] == nt
+            # the streamed tiles of a unit are covered exactly once, by at most THREE CTAs: the piece that starts at tile 0
+            # writes partial 0, a piece that neither starts nor ends the unit partial 1, the piece that ends it partial 2; the
+            # first piece clears the partials nobody writes (kernel: fill1 / fill2)
+            assert len(parts) <= 3 and parts[0][1] == 0 and parts[-1][2] == nt
             assert all(a[2] == b[1] for a, b in zip(parts, parts[1:]))
             assert len({p[0] for p in parts}) == len(parts)
+            written = set()
+            for cta, tb0, tb1 in parts:
+                first, last = tb0 == 0, tb1 == nt
+                part = 0 if first else (2 if last else 1)
+                assert part not in written
+                written.add(part)
+                if first:
+                    ul = u % upl
+                    next_reaches_end = Gl * (cta + 2) // grid >= (ul + 1) * nt      # TileRange::next_cta_reaches_end_of
+                    if last or next_reaches_end:
+                        assert 1 not in written
+                        written.add(1)
+                    if last:
+                        written.add(2)
+            assert written == {0, 1, 2}, "every partial plane of the unit is written exactly once"
         # batched launches cut every layer where a single-layer launch cuts it: bit-identical partial folds
         one, _ = _tile_ranges(H, nt, 1, grid, pair)
         for layer in range(layers):

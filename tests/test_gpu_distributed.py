@@ -80,11 +80,19 @@ def _worker(rank, world, port):
                         fn, extra = rd.pivot_update_kv_sharded, {"transport": transport}
                     kk, vv, pp, idx, hs = fn(q[:, g0 * G:(g0 + per[0]) * G], k[:, g0:g0 + per[0]], v[:, g0:g0 + per[0]], keep,
                                              per, mask, pos.clone(), rot, mrope, reforge, **extra)
-                    assert torch.equal(hs, cache.last_head_scores) and torch.equal(idx, cache.last_keep_indices), (transport, rep)
-                    assert torch.equal(kk, cache.layers[0].keys[:, g0:g0 + per[0]])
-                    assert torch.equal(vv, cache.layers[0].values[:, g0:g0 + per[0]])
-                    if reforge:
-                        assert torch.equal(pp, cache.position_cache[0])
+                    # per-head rows: last-bit differences against the full-width launch are possible (fp32 fold order of a
+                    # unit split between CTAs); the kept set is the single-GPU one or differs on the cut
+                    d = (hs.view(torch.int16).int() - cache.last_head_scores.view(torch.int16).int()).abs()
+                    assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-3, (transport, rep)
+                    from helpers import index_parity
+                    full_score = cache.last_head_scores.float().mean(0).to(torch.bfloat16).masked_fill(mask, 1.0)
+                    same, justified, _ = index_parity(idx, cache.last_keep_indices, full_score, keep)
+                    assert justified, (transport, rep)
+                    if same:
+                        assert torch.equal(kk, cache.layers[0].keys[:, g0:g0 + per[0]])
+                        assert torch.equal(vv, cache.layers[0].values[:, g0:g0 + per[0]])
+                        if reforge:
+                            assert torch.equal(pp, cache.position_cache[0])
             if rank == 0:
                 ex = rd.ScoreExchange.get(None, dev, KVH, L, "p2p")
                 print("score exchange transport:", ex.transport, flush=True)
@@ -106,10 +114,15 @@ def _worker(rank, world, port):
                     got = rd.pivot_update_batch_kv_sharded(
                         [(ql[:, g0 * G:(g0 + per[0]) * G], kl[:, g0:g0 + per[0]], vl[:, g0:g0 + per[0]], ml, pos.clone())
                          for ql, kl, vl, ml in data], keep, per, rot, mrope, reforge, transport=transport)
-                    for (kk, vv, pp, idx), (wk, wv, wp, widx, _) in zip(got, want):
-                        assert torch.equal(idx, widx), (transport, rep)
-                        assert torch.equal(kk, wk[:, g0:g0 + per[0]]) and torch.equal(vv, wv[:, g0:g0 + per[0]])
-                        assert torch.equal(pp, wp)
+                    for (kk, vv, pp, idx), (wk, wv, wp, widx, whs), (_, _, _, ml) in zip(got, want, data):
+                        full_score = whs.float().mean(0).to(torch.bfloat16)
+                        if ml is not None:
+                            full_score = full_score.masked_fill(ml, 1.0)
+                        same, justified, _ = index_parity(idx, widx, full_score, keep)
+                        assert justified, (transport, rep)
+                        if same:
+                            assert torch.equal(kk, wk[:, g0:g0 + per[0]]) and torch.equal(vv, wv[:, g0:g0 + per[0]])
+                            assert torch.equal(pp, wp)
     finally:
         dist.destroy_process_group()
 

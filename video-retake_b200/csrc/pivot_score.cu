@@ -142,9 +142,10 @@ struct ScoreParams {
     int n_atoms;                      // D / 64
     int q_dim1_is_l, k_dim1_is_l;     // tensor-map coordinate order (dims are sorted by stride on the host)
     float inv_sqrt_d;                 // fp32(1 / fp32(sqrt D))
-    float2* ml_part;                  // [2][H][nt*128]  pass 1 partial (row max in scaled-logit domain, row sum)
+    float2* ml_part;                  // [3][H][nt*128]  pass 1 partials (row max in scaled-logit domain, row sum): a unit is
+                                      //                 shared by at most three CTAs - first / middle / last part
     float* stats;                     // [H][nt*128]     c_q = m*log2e + log2(l)   (merge kernel output, pass 2 input)
-    float* colsum_part;               // [2][H][nt*128]  pass 2 partial fp32 sums over queries of bf16(P)
+    float* colsum_part;               // [3][H][nt*128]  pass 2 partial fp32 sums over queries of bf16(P)
 };
 
 constexpr float kLog2e = 1.4426950408889634f;
@@ -251,15 +252,23 @@ __device__ __forceinline__ void softmax_cols(uint32_t (&r)[64], int valid, Softm
 }
 
 // One CTA's share of the flattened (unit, streamed tile) space of a layer: a contiguous range, so every SM gets the same
-// number of tile-steps (+-1) and a unit is shared by at most two CTAs (range length >= nt).  With several layers in the
-// launch the CTA takes ITS range of every layer in turn - the cut points inside a layer are those of a single-layer
-// launch, so batched and per-layer scoring fold their fp32 partials in the same order and agree bit for bit.
+// number of tile-steps (+-1).  The host sizes the grid so that a range is at least half a unit long (floor(Gl / grid) >=
+// ceil(nt / 2)): a unit is then shared by at most THREE CTAs - the one with its first tiles, possibly a middle one, the one
+// with its last tiles - each writing its own partial plane.  (Launches with fewer units than SMs - a rank of the KV-head
+// split holds 7 heads = 112 units - still fill the machine that way.)  With several layers in the launch the CTA takes ITS
+// range of every layer in turn - the cut points inside a layer are those of a single-layer launch, so batched and
+// per-layer scoring fold their fp32 partials in the same order and agree bit for bit.
 struct TileRange {
     long long g, g1, Gl;
     int nt, layer, n_layers, units_per_layer;
     __device__ __forceinline__ void set_layer_range() {
         g = Gl * blockIdx.x / gridDim.x;
         g1 = Gl * (blockIdx.x + 1) / gridDim.x;
+    }
+    // does the NEXT CTA's range of the current layer reach the end of unit `u` (then the unit has no middle part)?
+    __device__ __forceinline__ bool next_cta_reaches_end_of(int u) const {
+        const int ul = u - layer * units_per_layer;
+        return Gl * (blockIdx.x + 2) / gridDim.x >= (long long)(ul + 1) * nt;
     }
     // H: heads of all layers, Hl: heads per layer; a head has ceil(nt / kPair) units of kPair stationary tiles
     __device__ __forceinline__ TileRange(int H, int Hl, int nt_) : nt(nt_), layer(0) {
@@ -453,8 +462,11 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
             float a0, a1;
             upk2(st.acc, a0, a1);
             if (PASS == 2) { a0 = st.c0; a1 = st.c1; }
-            const int part = (tb0 == 0) ? 0 : 1;
-            const bool whole = (tb0 == 0) && (tb1 == nt);
+            // this CTA's part of the unit: 0 = has its first tiles, 2 = has its last tiles (and not the first), 1 = in between.
+            // The CTA with the first tiles also writes the neutral element into the planes nobody else will write.
+            const bool first = (tb0 == 0), last = (tb1 == nt);
+            const int part = first ? 0 : (last ? 2 : 1);
+            const bool fill1 = first && (last || range.next_cta_reaches_end_of(u)), fill2 = first && last;
             const size_t o = (size_t)h * nt * kTile + (size_t)ta * kTile + row;
             const int g_lo = grp & ~1;               // the two groups of this stationary tile
             const bool folder = (grp == g_lo) && has_tile;
@@ -471,7 +483,8 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                         if (mg > -INFINITY) lt += merge[(g * kTile + row) * 2 + 1] * ex2f((mg - mn) * kLog2e);
                     }
                     prm.ml_part[(size_t)part * hl + o] = make_float2(mn, lt);
-                    if (whole) prm.ml_part[hl + o] = make_float2(-INFINITY, 0.f);
+                    if (fill1) prm.ml_part[hl + o] = make_float2(-INFINITY, 0.f);
+                    if (fill2) prm.ml_part[2 * hl + o] = make_float2(-INFINITY, 0.f);
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
             } else {
@@ -480,7 +493,8 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                 if (folder) {
                     const float cs = merge[g_lo * kTile + row] + merge[(g_lo + 1) * kTile + row];
                     prm.colsum_part[(size_t)part * hl + o] = cs;
-                    if (whole) prm.colsum_part[hl + o] = 0.f;
+                    if (fill1) prm.colsum_part[hl + o] = 0.f;
+                    if (fill2) prm.colsum_part[2 * hl + o] = 0.f;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(kSoftmaxWarps * 32) : "memory");
             }
@@ -491,18 +505,19 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
     if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// pass 1 epilogue: fold the (at most two) partial row statistics of every query into c_q = m*log2e + log2(l)
+// pass 1 epilogue: fold the (at most three) partial row statistics of every query into c_q = m*log2e + log2(l)
 __global__ void pivot_stats_merge_kernel(const float2* __restrict__ ml_part, int H, int L, int Lpad, float* __restrict__ stats) {
     pdl_enter();
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     const int h = blockIdx.y;
     if (q >= Lpad) return;
     const size_t o = (size_t)h * Lpad + q, hl = (size_t)H * Lpad;
-    const float2 p0 = ml_part[o], p1 = ml_part[hl + o];
-    const float mn = fmaxf(p0.x, p1.x);
+    const float2 p0 = ml_part[o], p1 = ml_part[hl + o], p2 = ml_part[2 * hl + o];
+    const float mn = fmaxf(fmaxf(p0.x, p1.x), p2.x);
     float lt = 0.f;
     if (p0.x > -INFINITY) lt += p0.y * ex2f((p0.x - mn) * kLog2e);
     if (p1.x > -INFINITY) lt += p1.y * ex2f((p1.x - mn) * kLog2e);
+    if (p2.x > -INFINITY) lt += p2.y * ex2f((p2.x - mn) * kLog2e);
     stats[o] = (q < L) ? fmaf(mn, kLog2e, lg2f(lt)) : INFINITY;
 }
 
@@ -523,7 +538,7 @@ __global__ void pivot_head_reduce_kernel(const float* __restrict__ colsum_part, 
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < G; ++j) {
         const size_t o = (size_t)(g * G + j) * Lpad + k;
-        v[j & 3] += round_bf16(colsum_part[o] + colsum_part[hl + o]);
+        v[j & 3] += round_bf16((colsum_part[o] + colsum_part[hl + o]) + colsum_part[2 * hl + o]);
     }
     const float s = ((v[0] + v[1]) + v[2]) + v[3];
     const int layer = g / out.KVH;
@@ -573,7 +588,7 @@ using namespace rtk;
 extern "C" size_t rtk_pivot_score_workspace_bytes(int64_t H, int64_t L) {
     if (H < 1 || L < 1) return 0;
     const size_t lpad = (size_t)((L + kTile - 1) / kTile) * kTile;
-    return 7 * (size_t)H * lpad * sizeof(float);       // ml_part (2 x float2) + stats + colsum_part (2)
+    return 10 * (size_t)H * lpad * sizeof(float);      // ml_part (3 x float2) + stats + colsum_part (3)
 }
 
 namespace rtk {
@@ -595,7 +610,9 @@ static int score_launch(const ScoreBatch& b, ScoreParams prm, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int units = prm.Hl * ((prm.nt + kPair - 1) / kPair);   // per layer: the grid (and so every cut point) is that of one layer
-    const int grid = units < sms ? units : sms;
+    // a CTA's range of a layer must be at least half a unit long (at most three CTAs per unit, see TileRange)
+    const long long gmax = (long long)units * prm.nt / ((prm.nt + 1) / 2);
+    const int grid = (int)(gmax < sms ? (gmax < 1 ? 1 : gmax) : sms);
     const size_t smem = ScoreSmem::total + 1024;
     cudaError_t e = cudaFuncSetAttribute(pivot_score_kernel<1, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -637,7 +654,7 @@ int pivot_score_batch(const ScoreBatch& b, void* workspace, size_t workspace_byt
     prm.inv_sqrt_d = 1.0f / sq;
     const size_t plane = (size_t)prm.H * prm.nt * kTile;
     prm.ml_part = reinterpret_cast<float2*>(workspace);
-    prm.stats = reinterpret_cast<float*>(workspace) + 4 * plane;
+    prm.stats = reinterpret_cast<float*>(workspace) + 6 * plane;
     prm.colsum_part = prm.stats + plane;
     return b.n == 1 ? score_launch<1>(b, prm, st) : score_launch<kMaxBatchLayers>(b, prm, st);
 }
