@@ -222,27 +222,23 @@ def run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer=None):
     cache = lc.build_kvcache(cache_config(s))
     pool = q.shape[0]
     it = 0
-    key = (pos_grid.data_ptr(), s.layers)
-    if getattr(run_step, "_pos_key", None) != key:
-        run_step._pos_key = key
-        run_step._pos_buf = pos_grid[None].repeat(s.layers, *([1] * pos_grid.dim())).contiguous()
-        run_step._pos_first_p1 = (pos_grid[0] + 1).contiguous()
-    pos_buf, pos_first_p1 = run_step._pos_buf, run_step._pos_first_p1
+
     for c in range(s.chunks):
         ss, ee = c * s.L, min((c + 1) * s.L, s.tokens)
         Lc = ee - ss
         cache.kvcache_compression = True
         cache.keypatches_mask_chunk = mask[ss:ee]            # (LLaVA: only the first t*196 of the t*729 entries land on tokens)
+        # the caller's re-basing of the temporal ids (the attention forward continues them after each layer's compacted
+        # cache, qwen2_vl.py:68-73) for all layers of the chunk at once - what this repo's model glue does as well
+        if s.reforge:
+            pos_all = cache.rebased_position_ids(pos_grid[..., :Lc], s.layers)
+        else:
+            pos_all = pos_grid[..., :Lc].unsqueeze(0).repeat(s.layers, *([1] * pos_grid.dim()))
+            pos_all[:, 0] += c * (s.L // s.tok_per_grid if s.mrope else s.L)
         for layer in range(s.layers):
             j = it % pool
             it += 1
-            # the glue's per-layer re-basing of the temporal ids (qwen2_vl.py:68-73) as ONE small kernel: rows 1, 2 of the
-            # layer's id buffer are constant, row 0 = grid ids + 1 + (this layer's last kept temporal id)
-            pos = pos_buf[layer][..., :Lc]
-            if s.reforge:
-                torch.add(pos_first_p1[..., :Lc], cache.get_prev_temporal_idx(layer), out=pos[0])
-            else:
-                torch.add(pos_grid[0][..., :Lc], c * (s.L // s.tok_per_grid if s.mrope else s.L), out=pos[0])
+            pos = pos_all[layer]
             if timer is not None and not s.deferred:
                 timer.arm(cache)
             cache.update(k[j:j + 1, :Lc].transpose(1, 2), v[j:j + 1, :Lc].transpose(1, 2), layer,

@@ -93,3 +93,78 @@ def test_build_kvcache_factory():
     cfg.longvideo_kwargs["kvcache_compression_kwargs"]["compression_method"] = "h2o"
     with pytest.raises(NotImplementedError):
         build_kvcache(cfg)
+
+
+def test_build_id_matches_sources_and_stale_library_is_refused(monkeypatch):
+    """nothing used to prove which sources a tested library came from.  The library carries the hash of its
+    sources; the binding refuses an in-tree library built from other sources."""
+    import importlib.util
+    from retake import _native
+    lib = _native.lib()
+    spec = importlib.util.spec_from_file_location("rtk_build_t", os.path.join(ROOT, "video-retake_b200", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    sid = mod.source_id()
+    assert len(sid) == 16 and lib.rtk_build_id().decode() == sid == _native.build_id()
+    assert mod.built_id() == sid                                    # lib/BUILD_ID written next to the .so
+    monkeypatch.delenv("RTK_B200_LIB", raising=False)
+    monkeypatch.delenv("RTK_ALLOW_STALE_LIB", raising=False)
+    monkeypatch.setattr(_native, "_source_id", lambda: "0123456789abcdef")
+    with pytest.raises(_native.RtkError, match="built from other sources"):
+        _native._check_build_id(lib)
+    monkeypatch.setenv("RTK_ALLOW_STALE_LIB", "1")
+    _native._check_build_id(lib)                                    # explicit opt-out
+    # the SASS summary of the build names the Blackwell opcodes of the scoring object
+    import json
+    sass = json.load(open(os.path.join(ROOT, "video-retake_b200", "lib", "SASS_SUMMARY.json")))
+    assert sass["build_id"] == sid
+    ops = sass["opcodes"]["pivot_score.o"]
+    assert ops.get("UTCHMMA", 0) > 0 and ops.get("UTMALDG", 0) > 0 and ops.get("LDTM", 0) > 0
+    assert sass["opcodes"]["dpselect.o"].get("UBLKCP", 0) > 0
+
+
+def test_real_reference_loader_agrees_with_the_port():
+    """bench.py's CPU arm: the unmodified reference functions (when a reference tree is around) and the op-sequence port
+    give the same bits on a small case"""
+    from oracle import real_reference, reference_ops as ro
+    real = real_reference.load()
+    if real is None:
+        pytest.skip("no reference tree (RETAKE_REFERENCE, baseline/_ref, /root/reference)")
+    vc_ref, cache_cls, base = real
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 12, 6, 64, generator=g).to(torch.bfloat16)
+    out, mask = vc_ref.memory_bank_compress_keyframe(x.clone(), 5, 3, sync=False)
+    pout, pmask, _ = ro.dpselect(x.clone(), 5, False)
+    assert torch.equal(out, pout) and torch.equal(mask, pmask)
+    H, KVH, D, L = 4, 2, 32, 48
+    q = torch.randn(1, H, L, D, generator=g).to(torch.bfloat16)
+    k = torch.randn(1, KVH, L, D, generator=g).to(torch.bfloat16)
+    v = torch.randn(1, KVH, L, D, generator=g).to(torch.bfloat16)
+    cache = cache_cls(real_reference.llm_config(H, KVH, D, 1, 0.5, False))
+    cache.kvcache_compression = True
+    cache.update(k, v, 0, {"query_states": q, "position_ids": torch.arange(L)[None], "rotary_emb": None, "mrope_section": None})
+    kk, vv, _, idx, _ = ro.pivot_update(q, k, v, 0.5)
+    assert torch.equal(cache.layers[0].keys, kk) and torch.equal(cache.layers[0].values, vv)
+
+
+def test_bench_traffic_record_is_tied_to_the_scoring_source(tmp_path, monkeypatch):
+    import hashlib
+    import json
+    import types
+    import bench
+    sha = hashlib.sha256(open(os.path.join(ROOT, "video-retake_b200", "csrc", "pivot_score.cu"), "rb").read()).hexdigest()[:16]
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    (tmp_path / "video-retake_b200" / "csrc").mkdir(parents=True)
+    (tmp_path / "video-retake_b200" / "csrc" / "pivot_score.cu").write_bytes(
+        open(os.path.join(ROOT, "video-retake_b200", "csrc", "pivot_score.cu"), "rb").read())
+    s = types.SimpleNamespace(L=4096, deferred=True)
+    assert bench.measured_traffic(s) is None                          # no record at all
+    (prof / "ncu_score_traffic.json").write_text(json.dumps([{"score_source_sha": "stale", "L": 4096, "deferred": True,
+                                                               "bytes_per_layer": 1.0}]))
+    assert bench.measured_traffic(s) is None                          # a capture of another kernel is never used
+    (prof / "ncu_score_traffic.json").write_text(json.dumps([{"score_source_sha": sha, "L": 4096, "deferred": True,
+                                                               "bytes_per_layer": 7.0e7}]))
+    assert bench.measured_traffic(s) == 7.0e7
+    assert bench.measured_traffic(types.SimpleNamespace(L=6272, deferred=True)) is None

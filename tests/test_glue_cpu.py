@@ -135,3 +135,40 @@ def test_score_kernel_partition_invariants():
         for cta, layer, u, tb0, tb1 in steps:
             per[(cta, layer)] = per.get((cta, layer), 0) + tb1 - tb0
         assert max(per.values()) - min(per.values()) <= 1
+
+
+def test_rebased_position_ids_equal_the_per_layer_rule():
+    """PivotKVCache.rebased_position_ids: the ids of a chunk for all layers at once == the attention forward's per-layer
+    `ids[0] += prev_l + 1 - ids[0, ..., 0]` (reference qwen2_vl.py:68-73, llava_onevision.py:80-89)"""
+    import types
+    from retake.longvideo_cache import PivotKVCache
+    cfg = types.SimpleNamespace(hidden_size=64, num_hidden_layers=3, num_attention_heads=4, num_key_value_heads=2)
+    cfg.longvideo_kwargs = {"kvcache_compression": True, "kvcache_compression_kwargs": {
+        "compression_ratio": 0.5, "compression_method": "pivotkv", "pos_embed_reforge": True}}
+    for mrope in (True, False):
+        cache = PivotKVCache(cfg)
+        L = 10
+        ar = torch.arange(L)
+        pos = torch.stack([40 + ar // 4, ar % 4, ar % 2])[:, None] if mrope else (40 + ar)[None]
+        # empty cache: every layer starts at temporal id 0
+        got = cache.rebased_position_ids(pos, 3)
+        for layer in range(3):
+            want = pos.clone()
+            want[0] += -1 + 1 - pos[0].reshape(-1)[0]
+            assert torch.equal(got[layer], want)
+        # layers whose caches end at different temporal ids
+        for layer, last in enumerate((7, 3, 11)):
+            if mrope:
+                kept = torch.stack([torch.tensor([0, 2, last]), torch.tensor([0, 1, 1]), torch.tensor([0, 0, 1])])[:, None]
+            else:
+                kept = torch.tensor([[0, 2, last]])
+            cache.update_position_ids(kept, layer)
+        got = cache.rebased_position_ids(pos, 3)
+        assert got.shape == (3,) + tuple(pos.shape)
+        for layer, last in enumerate((7, 3, 11)):
+            want = pos.clone()
+            want[0] += last + 1 - pos[0].reshape(-1)[0]
+            assert torch.equal(got[layer], want)
+            assert int(got[layer][0].reshape(-1)[0]) == last + 1
+        got[0][0] += 1000                                            # a layer's slice is its own memory
+        assert int(got[1][0].reshape(-1)[0]) == 3 + 1

@@ -189,7 +189,8 @@ class ScoreExchange:
     def get(cls, group, device, rows: int, L: int, transport: Optional[str] = None):
         import os
         transport = transport or os.environ.get("RTK_SHARD_TRANSPORT", "p2p")
-        key = (id(group) if group is not None else 0, device, transport)
+        # keyed by the ranks of the group (an id() could be recycled by another group object)
+        key = (tuple(dist.get_process_group_ranks(group if group is not None else dist.group.WORLD)), device, transport)
         ex = cls._cache.get(key)
         if ex is None or ex.capacity < rows * L:
             ex = cls._cache[key] = cls(group, device, max(rows * L, 8 * 16384), transport)
@@ -238,7 +239,8 @@ def pivot_update_kv_sharded(query_local, key_local, value_local, keep_len: int, 
 
     ``query_local [1, G * KVH_local, L, D]`` are the query heads of this rank's KV groups.  Returns
     ``(kept_k [1, KVH_local, keep, D], kept_v, kept_positions, keep_idx, head_scores [KVH, L])``; ``keep_idx`` is
-    identical on every rank.
+    identical on every rank.  ``head_scores`` is a VIEW of the exchange buffer: valid until the next update but one on
+    this group (clone it to keep it).
 
     Two C-ABI calls around one exchange of the ``[KVH_local, L]`` score rows (``rtk_pivot_update`` with ``skip_select``,
     then with ``skip_score``): un-rotate + score + put | wait + select + compact + re-rotate, eight launches, the rows

@@ -677,6 +677,25 @@ class PivotKVCache(DynamicCache):
         cache_layer = self.position_cache[layer_idx]
         return cache_layer[0, 0, -1] if cache_layer.ndim == 3 else cache_layer[0, -1]
 
+    def rebased_position_ids(self, position_ids: torch.Tensor, n_layers: int) -> torch.Tensor:
+        """The ids a new chunk gets in EVERY layer, in a handful of launches: the attention forward continues the temporal
+        row after each layer's compacted cache (``ids[0] += prev_l + 1 - ids[0, ..., 0]``, reference ``qwen2_vl.py:68-73`` /
+        ``llava_onevision.py:80-89``); at the start of a chunk the previous chunk is settled in all layers, so the ``prev_l``
+        are all known.  ``position_ids`` ``[3, 1, L]`` or ``[1, L]`` -> ``[n_layers, 3, 1, L]`` / ``[n_layers, 1, L]``; layer
+        l's slice is a tensor of its own (it can be handed to ``update`` with ``position_ids_owned``)."""
+        prevs = [self.get_prev_temporal_idx(l) for l in range(n_layers)]
+        dev = position_ids.device
+        if all(not isinstance(p, torch.Tensor) for p in prevs):
+            prev = torch.tensor([int(p) for p in prevs], dtype=position_ids.dtype, device=dev)
+        else:
+            prev = torch.stack([p if isinstance(p, torch.Tensor) else torch.tensor(int(p), dtype=position_ids.dtype, device=dev)
+                                for p in prevs])
+        out = position_ids.unsqueeze(0).repeat(n_layers, *([1] * position_ids.dim()))
+        first = position_ids[0].reshape(-1)[0]
+        t = out[:, 0]                                                  # the temporal rows of all layers
+        t += (prev + (1 - first)).view(-1, *([1] * (t.dim() - 1)))
+        return out
+
     def get_seq_length(self, layer_idx: int = 0) -> int:
         if layer_idx >= len(self.layers):
             return 0

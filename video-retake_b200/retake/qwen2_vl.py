@@ -57,12 +57,17 @@ def retake_Qwen2VLAttention_forward(self, hidden_states, attention_mask=None, po
     if isinstance(cache, PivotKVCache) and cache.pos_embed_reforge and pos3d is not None and rotary is not None:
         # temporal ids continue after this layer's (compacted) cache; sync-free form of qwen2_vl.py:68-73
         assert bsz == 1
-        # (out of place: every layer gets ITS OWN id tensor, handed over to the cache - deferred compression reads it at
-        #  after_forward() - and the next layer re-bases relative to it, exactly like the reference's in-place update)
-        prev = cache.get_prev_temporal_idx(self.layer_idx)
-        shifted = pos3d.clone()
-        shifted[0, 0, :] += prev + 1 - pos3d[0, 0, 0]
-        pos3d = cache.retake_position_ids = shifted
+        # Every layer gets ITS OWN id tensor (handed over to the cache: deferred compression reads it at after_forward()).
+        # The re-basing only depends on the layer's cache as the previous call left it, so _lm() has computed the ids of
+        # all layers up front (PivotKVCache.rebased_position_ids: a handful of launches per call instead of a few per layer).
+        pos_all = getattr(cache, "retake_position_ids_all", None)
+        if pos_all is not None and self.layer_idx < pos_all.shape[0]:
+            pos3d = pos_all[self.layer_idx]
+        else:
+            prev = cache.get_prev_temporal_idx(self.layer_idx)
+            shifted = pos3d.clone()
+            shifted[0, 0, :] += prev + 1 - pos3d[0, 0, 0]
+            pos3d = cache.retake_position_ids = shifted
         cos, sin = rotary(value_states, pos3d)
     else:
         cos, sin = position_embeddings
@@ -216,6 +221,9 @@ def _video_features(self, pixel_values_videos, video_grid_thw):
 def _lm(self, cache, inputs_embeds, position_ids, **kwargs):
     """one language-model call; the 3-D ids of this call ride on the cache for the per-layer rotary"""
     cache.retake_position_ids = position_ids.clone() if isinstance(cache, PivotKVCache) else None
+    cache.retake_position_ids_all = None
+    if isinstance(cache, PivotKVCache) and cache.pos_embed_reforge:
+        cache.retake_position_ids_all = cache.rebased_position_ids(position_ids, self.language_model.config.num_hidden_layers)
     cache.retake_rotary_emb = self.language_model.rotary_emb
     return self.language_model(input_ids=None, position_ids=position_ids, attention_mask=None, past_key_values=cache,
                                inputs_embeds=inputs_embeds, use_cache=True, **kwargs)
