@@ -55,9 +55,13 @@ def retake_Qwen2Attention_forward(self, hidden_states, position_embeddings, atte
     position_ids = None
     if isinstance(cache, PivotKVCache) and cache.pos_embed_reforge and pos is not None and rotary is not None:
         # re-base this chunk's positions on the layer's compacted cache (sync-free form of reference :80-89)
-        prev = cache.get_prev_temporal_idx(self.layer_idx)
-        position_ids = pos.clone()
-        position_ids[0, :] += prev + 1 - pos[0, 0]
+        pos_all = getattr(cache, "retake_position_ids_all", None)
+        if pos_all is not None and self.layer_idx < pos_all.shape[0]:
+            position_ids = pos_all[self.layer_idx]          # all layers re-based up front by _lm()
+        else:
+            prev = cache.get_prev_temporal_idx(self.layer_idx)
+            position_ids = pos.clone()
+            position_ids[0, :] += prev + 1 - pos[0, 0]
         cos, sin = rotary(value_states, position_ids)
     else:
         cos, sin = position_embeddings
@@ -185,6 +189,9 @@ def _siglip_features(self, pixel_values_videos, vision_feature_layer):
 
 def _lm(self, cache, inputs_embeds, position_ids, **kwargs):
     cache.retake_position_ids = position_ids if isinstance(cache, PivotKVCache) else None
+    cache.retake_position_ids_all = None
+    if isinstance(cache, PivotKVCache) and cache.pos_embed_reforge and position_ids is not None:
+        cache.retake_position_ids_all = cache.rebased_position_ids(position_ids, self.language_model.config.num_hidden_layers)
     cache.retake_rotary_emb = self.language_model.rotary_emb
     return self.language_model(attention_mask=None, position_ids=position_ids, past_key_values=cache,
                                inputs_embeds=inputs_embeds, use_cache=True, **kwargs)
