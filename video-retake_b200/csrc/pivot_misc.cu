@@ -858,6 +858,10 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
             return RTK_E_BADARG;
         for (int r = 0; r < a->xchg_world; ++r)
             if (!a->xchg_scores[r] || !a->xchg_flags[r]) return RTK_E_BADARG;
+        // where the rows live is part of the protocol: checked before anything is launched
+        const char* own = (const char*)a->xchg_scores[a->xchg_rank];
+        if (a->skip_select && (const char*)a->head_scores != own + (size_t)a->xchg_rank * KVH * L * 2) return RTK_E_BADARG;
+        if (a->skip_score && (const char*)a->head_scores != own) return RTK_E_BADARG;
     }
     const int64_t score_rows = a->score_rows > 0 ? a->score_rows : KVH;
     if (a->reforge) {
@@ -907,7 +911,6 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
             xp.src = (const __nv_bfloat16*)a->head_scores;
             xp.n = (long long)KVH * L;
             xp.world = a->xchg_world; xp.rank = a->xchg_rank; xp.epoch = a->xchg_epoch;
-            if (xp.src != (const __nv_bfloat16*)a->xchg_scores[a->xchg_rank] + (size_t)a->xchg_rank * KVH * L) return RTK_E_BADARG;
             for (int r = 0; r < a->xchg_world; ++r) {
                 xp.dst[r] = (__nv_bfloat16*)a->xchg_scores[r] + (size_t)a->xchg_rank * KVH * L;
                 xp.flags[r] = a->xchg_flags[r];
@@ -922,7 +925,6 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
         const size_t smem = (size_t)L * 4 + 112 * 4;
         cudaError_t e = cudaFuncSetAttribute(pivot_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
-        if (xchg && a->head_scores != a->xchg_scores[a->xchg_rank]) return RTK_E_BADARG;
         RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream, (const __nv_bfloat16*)a->head_scores,
                        (int)score_rows, (int)L, a->keymask, (int)a->keep, a->keep_idx, (__nv_bfloat16*)nullptr,
                        (const long long*)(a->reforge ? a->pos : nullptr), a->reforge ? tmin : (long long*)nullptr,
@@ -1040,7 +1042,6 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
             xp.n = (long long)KVH * L; xp.world = a0.xchg_world; xp.rank = a0.xchg_rank;
             for (int i = 0; i < n; ++i) {
                 xp.src[i] = (const __nv_bfloat16*)a[i].head_scores;
-                if (xp.src[i] != (const __nv_bfloat16*)a[i].xchg_scores[a0.xchg_rank] + (size_t)a0.xchg_rank * KVH * L) return RTK_E_BADARG;
                 for (int r = 0; r < a0.xchg_world; ++r)
                     xp.dst[i][r] = (__nv_bfloat16*)a[i].xchg_scores[r] + (size_t)a0.xchg_rank * KVH * L;
             }
@@ -1104,7 +1105,11 @@ extern "C" int rtk_pivot_update_batch(const rtk_pivot_update_args* layers, int64
         if (a0.xchg_world > 1)
             for (int r = 0; r < a0.xchg_world; ++r)
                 if (!x.xchg_scores[r] || !a0.xchg_flags[r]) return RTK_E_BADARG;
-        if (a0.xchg_world > 1 && a0.skip_score && x.head_scores != x.xchg_scores[a0.xchg_rank]) return RTK_E_BADARG;
+        if (a0.xchg_world > 1) {
+            const char* own = (const char*)x.xchg_scores[a0.xchg_rank];
+            if (a0.skip_score && (const char*)x.head_scores != own) return RTK_E_BADARG;
+            if (a0.skip_select && (const char*)x.head_scores != own + (size_t)a0.xchg_rank * a0.KVH * a0.L * 2) return RTK_E_BADARG;
+        }
         if (x.pos && (!x.pos_out || x.n_pos < 1 || x.n_pos > 3)) return RTK_E_BADARG;
         if ((((uintptr_t)x.q | (uintptr_t)x.k | (uintptr_t)x.v | (uintptr_t)x.k_out | (uintptr_t)x.v_out) & 15u) != 0) return RTK_E_ALIGN;
         if ((x.q_stride_h | x.q_stride_l | x.k_stride_h | x.k_stride_l | x.v_stride_h | x.v_stride_l | x.out_stride_h) % 8 != 0)
