@@ -634,6 +634,11 @@ def main():
     # kept-index parity self-check and the r_v = 0.5 DPSelect figure: BEFORE the warm-up, so that the warm-up steps leave
     # the caching allocator in the state the timed steps find
     parity = dps_half = None
+    key_patch_share = None
+    if rank == 0:
+        _, kp_mask = vc.memory_bank_compress_keyframe(x[None], s.t, 3, sync=False)
+        key_patch_share = float(kp_mask[:s.tokens].float().mean())       # the keys pass 2 of the scoring skips
+        del kp_mask
     if rank == 0 and not a.no_parity:
         _, kp_mask = vc.memory_bank_compress_keyframe(x[None], s.t, 3, sync=False)
         parity = parity_record(s, q, k, v, rotary, lc, pos_grid, kp_mask)
@@ -769,21 +774,27 @@ def main():
     score_ms = timer.mean_ms()
     flops = 2.0 * s.H * s.L * s.L * s.D
     achieved = flops / (score_ms * 1e-3) / 1e12 if score_ms > 0 else 0.0
+    elide = os.environ.get("RTK_NO_KEY_ELISION") != "1"
+    executed = 2.0 - (key_patch_share if (elide and key_patch_share is not None) else 0.0)
     roofline = {"kernel": ("pivot_score_kernel<1> + pivot_score_kernel<2> (the scoring of one layer; timed around the batched "
                            f"scoring of a chunk's {s.layers} layers, divided by {s.layers})") if s.deferred else
                           "pivot_score_kernel<1> + pivot_score_kernel<2> (one rtk_pivot_score call)", "bound": "tensor",
                 "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "achieved_executed": 2 * achieved, "frac_executed": 2 * achieved / peak_tf, "peak_source": peak_src,
+                # pass 1 contracts every (query, key) pair, pass 2 only the keys that are not key patches (their score is
+                # overwritten with 1.0 before the top-k, longvideo_cache.py:272-274)
+                "key_patch_share": key_patch_share, "executed_over_algorithmic": executed,
+                "achieved_executed": executed * achieved, "frac_executed": executed * achieved / peak_tf, "peak_source": peak_src,
                 "ms_per_call": score_ms, "calls_timed": len(timer.pairs),
                 # dram__bytes_read.sum + dram__bytes_write.sum of both launches per layer from the committed `ncu --set full`
                 # capture - used only when that capture was taken from THIS build and shape, else null (never a stale constant)
                 "traffic": measured_traffic(s),
                 # an exact two-pass softmax needs 2*H*L^2 fp32 ex2; B200 issues 16 MUFU per clock and SM
-                "xu_floor_ms": 2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3,
-                "frac_of_xu_floor": (2.0 * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3) / score_ms if score_ms > 0 else 0.0,
-                "note": ("algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it twice and is bounded by "
-                         "MUFU.EX2 throughput and the softmax warps' instruction stream (XU pipe 73-76 % busy; xu_floor_ms = "
-                         "2*H*L^2 exps at 16/clk/SM, 1.9 GHz), not by the tensor pipe (36 % busy); the kernel also holds the board at its "
+                "xu_floor_ms": executed * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3,
+                "frac_of_xu_floor": (executed * s.H * s.L * s.L / (16.0 * 148 * 1.9e9) * 1e3) / score_ms if score_ms > 0 else 0.0,
+                "note": ("algorithmic = ONE Q.K^T (2*H*L^2*D); the exact two-pass softmax executes it once for the row statistics and "
+                         "once more for the keys that are not key patches, and is bounded by "
+                         "MUFU.EX2 throughput and the softmax warps' instruction stream (XU pipe 76-79 % busy; xu_floor_ms = "
+                         "executed_over_algorithmic*H*L^2 exps at 16/clk/SM, 1.9 GHz), not by the tensor pipe (37 % busy); the kernel also holds the board at its "
                          "1 kW power cap (clocks.reasons sw_power_cap; profiles/r1_score_power_probe.json: the TMA + MMA feeder alone "
                          "needs 0.245 ms per call at 1 kW) - DESIGN.md section 5")}
     dps_ms = sum(a.elapsed_time(b) for a, b in timer.dpselect) / max(1, len(timer.dpselect))

@@ -69,40 +69,53 @@ def test_llava_helpers():
 # ---------------------------------------------------------------------------------------------------------------------
 # Work partition of the scoring kernels (csrc/pivot_score.cu, struct TileRange) restated in Python: the invariants the
 # kernel's partial-result protocol relies on, over the shapes the tests and the benchmark use.
-def _tile_ranges(heads_per_layer, nt, layers, grid, pair):
-    """[(cta, layer, unit, tb0, tb1)] in the order a CTA walks them (TileRange::next)"""
-    nta = (nt + pair - 1) // pair
-    units_per_layer = heads_per_layer * nta
-    Gl = units_per_layer * nt
-    out = []
+def _tile_ranges(heads_per_layer, nt, layers, grid, pair, nt_a_per_layer=None):
+    """[(cta, layer, unit-of-layer, tb0, tb1)] in the order a CTA walks them (TileRange::next); ``nt_a_per_layer``: stationary
+    tiles per layer when pass 2 elides the key patches (default: nt, every key)"""
+    out, meta = [], []
+    for layer in range(layers):
+        nt_a = nt if nt_a_per_layer is None else nt_a_per_layer[layer]
+        nta = (nt_a + pair - 1) // pair
+        Gl = heads_per_layer * nta * nt
+        geff = max(1, min(grid, Gl // ((nt + 1) // 2)))
+        meta.append((nta, Gl, geff))
     for cta in range(grid):
         for layer in range(layers):
-            g, g1 = Gl * cta // grid, Gl * (cta + 1) // grid
+            nta, Gl, geff = meta[layer]
+            if cta >= geff:
+                continue
+            g, g1 = Gl * cta // geff, Gl * (cta + 1) // geff
             while g < g1:
                 ul = g // nt
                 tb0 = g - ul * nt
                 tb1 = min(nt, tb0 + (g1 - g))
-                out.append((cta, layer, layer * units_per_layer + ul, tb0, tb1))
+                out.append((cta, layer, ul, tb0, tb1))
                 g += tb1 - tb0
-    return out, units_per_layer
+    return out, meta
 
 
 def test_score_kernel_partition_invariants():
     import itertools
-    for (H, nt, layers), pair in itertools.product([(28, 32, 1), (28, 32, 28), (28, 49, 3), (4, 8, 2), (4, 1, 5), (14, 1, 1), (8, 2, 33),
-                                                    (28, 18, 2), (2, 3, 1), (7, 32, 28), (14, 32, 2), (7, 49, 1), (1, 5, 1)], (1, 2)):
-        nta = (nt + pair - 1) // pair
-        # host side (score_launch): one layer's units decide the grid; a range is at least half a unit long, so launches
-        # with fewer units than SMs (7 heads per rank of the KV-head split) still use the whole machine
-        grid = max(1, min(H * nta * nt // ((nt + 1) // 2), 148))
-        steps, upl = _tile_ranges(H, nt, layers, grid, pair)
-        Gl = upl * nt
+    shapes = [(28, 32, 1, None), (28, 32, 28, None), (28, 49, 3, None), (4, 8, 2, None), (4, 1, 5, None), (14, 1, 1, None),
+              (8, 2, 33, None), (28, 18, 2, None), (2, 3, 1, None), (7, 32, 28, None), (14, 32, 2, None), (7, 49, 1, None),
+              (1, 5, 1, None),
+              # pass 2 with key elision: fewer stationary tiles than streamed ones, different per layer, down to none
+              (28, 32, 3, [23, 22, 24]), (7, 32, 4, [23, 1, 0, 32]), (4, 8, 3, [5, 8, 1]), (28, 49, 2, [35, 2]), (2, 3, 2, [1, 0])]
+    for (H, nt, layers, nt_a), pair in itertools.product(shapes, (1, 2)):
+        nta_full = (nt + pair - 1) // pair
+        # host side (score_launch): one layer's units AT THE FULL KEY COUNT decide the grid; a range is at least half a unit
+        # long, so launches with fewer units than SMs (7 heads per rank of the KV-head split) still use the whole machine
+        grid = max(1, min(H * nta_full * nt // ((nt + 1) // 2), 148))
+        steps, meta = _tile_ranges(H, nt, layers, grid, pair, nt_a)
         seen = {}
-        for cta, layer, u, tb0, tb1 in steps:
-            assert 0 <= tb0 < tb1 <= nt and layer * upl <= u < (layer + 1) * upl
-            seen.setdefault(u, []).append((cta, tb0, tb1))
-        assert sorted(seen) == list(range(layers * upl)), "every unit of every layer is visited"
-        for u, parts in seen.items():
+        for cta, layer, ul, tb0, tb1 in steps:
+            nta, Gl, geff = meta[layer]
+            assert 0 <= tb0 < tb1 <= nt and 0 <= ul < H * nta
+            seen.setdefault((layer, ul), []).append((cta, tb0, tb1))
+        want_units = [(layer, ul) for layer in range(layers) for ul in range(H * meta[layer][0])]
+        assert sorted(seen) == want_units, "every unit of every layer is visited (and nothing else)"
+        for (layer, ul), parts in seen.items():
+            nta, Gl, geff = meta[layer]
             parts.sort(key=lambda p: p[1])
             # the streamed tiles of a unit are covered exactly once, by at most THREE CTAs: the piece that starts at tile 0
             # writes partial 0, a piece that neither starts nor ends the unit partial 1, the piece that ends it partial 2; the
@@ -117,24 +130,26 @@ def test_score_kernel_partition_invariants():
                 assert part not in written
                 written.add(part)
                 if first:
-                    ul = u % upl
-                    next_reaches_end = Gl * (cta + 2) // grid >= (ul + 1) * nt      # TileRange::next_cta_reaches_end_of
+                    next_reaches_end = Gl * (cta + 2) // geff >= (ul + 1) * nt      # TileRange::next_cta_reaches_end_of
                     if last or next_reaches_end:
                         assert 1 not in written
                         written.add(1)
                     if last:
                         written.add(2)
             assert written == {0, 1, 2}, "every partial plane of the unit is written exactly once"
-        # batched launches cut every layer where a single-layer launch cuts it: bit-identical partial folds
-        one, _ = _tile_ranges(H, nt, 1, grid, pair)
+        # batched launches cut every layer where a single-layer launch (of that layer's key count) cuts it
         for layer in range(layers):
-            mine = [(c, u - layer * upl, a, b) for c, l, u, a, b in steps if l == layer]
+            one, _ = _tile_ranges(H, nt, 1, grid, pair, None if nt_a is None else [nt_a[layer]])
+            mine = [(c, u, a, b) for c, l, u, a, b in steps if l == layer]
             assert mine == [(c, u, a, b) for c, _, u, a, b in one]
-        # every CTA gets the same number of tile-steps per layer, +-1
-        per = {}
-        for cta, layer, u, tb0, tb1 in steps:
-            per[(cta, layer)] = per.get((cta, layer), 0) + tb1 - tb0
-        assert max(per.values()) - min(per.values()) <= 1
+        # every CTA that takes part in a layer gets the same number of tile-steps, +-1
+        for layer in range(layers):
+            per = {}
+            for cta, l, u, tb0, tb1 in steps:
+                if l == layer:
+                    per[cta] = per.get(cta, 0) + tb1 - tb0
+            if per:
+                assert len(per) == min(meta[layer][2], sum(1 for _ in per)) and max(per.values()) - min(per.values()) <= 1
 
 
 def test_rebased_position_ids_equal_the_per_layer_rule():

@@ -279,6 +279,96 @@ pivot_rope_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __re
     }
 }
 
+// ================================================================================= key elision (pass 2 of the scoring)
+// Key-patch tokens get score 1.0 whatever their column sum is (longvideo_cache.py:272-274 overwrites it before the top-k), so
+// the second pass of the scoring - one exp per (query, key) - only has to visit the other keys.  Two small kernels prepare
+// that: an exclusive scan of the mask (slot[j] = row of key j among the keys that are NOT key patches, -1 for a key patch;
+// n_keys = how many there are) and a gather of those K rows into a compact, token-major copy that pass 2 keeps stationary.
+bool key_elision_enabled();
+
+struct KeyElide {
+    const uint8_t* keymask[kMaxBatchLayers];     // [L] or nullptr (no key patches: identity)
+    int32_t* slot[kMaxBatchLayers];              // [L]
+    const __nv_bfloat16* k[kMaxBatchLayers];     // the K rows the scoring uses (un-rotated copy, or the caller's view)
+    long long k_stride_h[kMaxBatchLayers], k_stride_l[kMaxBatchLayers];
+    __nv_bfloat16* kc[kMaxBatchLayers];          // [n_keys, KVH, D]
+    int32_t* n_keys;                             // [layers]
+    int L, KVH, D;
+};
+
+__global__ void __launch_bounds__(1024)
+pivot_keymask_scan_kernel(const __grid_constant__ KeyElide e) {
+    pdl_enter();
+    __shared__ int wsum[32];
+    const int layer = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint8_t* __restrict__ m = e.keymask[layer];
+    int32_t* __restrict__ slot = e.slot[layer];
+    const int per = (e.L + 1023) / 1024;
+    const int beg = min(tid * per, e.L), end = min(beg + per, e.L);
+    int cnt = 0;
+    for (int i = beg; i < end; ++i) cnt += !(m && m[i]);
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += n;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = wsum[lane];
+        int winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int n = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += n;
+        }
+        wsum[lane] = winc - w;                               // exclusive over warps
+        if (lane == 31) e.n_keys[layer] = winc;
+    }
+    __syncthreads();
+    int base = wsum[warp] + inc - cnt;
+    for (int i = beg; i < end; ++i) slot[i] = (m && m[i]) ? -1 : base++;
+}
+
+__global__ void __launch_bounds__(256)
+pivot_keys_compact_kernel(const __grid_constant__ KeyElide e) {
+    pdl_enter();
+    const int layer = blockIdx.y;
+    const int vpr = e.D >> 3;
+    const long long total = (long long)e.L * e.KVH * vpr;
+    const int32_t* __restrict__ slot = e.slot[layer];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int v = (int)(i % vpr);
+        const long long lh = i / vpr;
+        const int h = (int)(lh % e.KVH);
+        const int l = (int)(lh / e.KVH);
+        const int sl = slot[l];
+        if (sl < 0) continue;
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(e.k[layer] + h * e.k_stride_h[layer] + l * e.k_stride_l[layer] + v * 8));
+        *reinterpret_cast<uint4*>(e.kc[layer] + ((size_t)sl * e.KVH + h) * e.D + v * 8) = w;
+    }
+}
+
+// scan + gather for the layers of one launch; fills the elision fields of the scoring batch
+static int key_elide_prepare(KeyElide& ke, int n, ScoreBatch& sb, cudaStream_t st) {
+    RTK_LAUNCH_PDL(pivot_keymask_scan_kernel, (unsigned)n, 1024, 0, st, ke);
+    const long long total = (long long)ke.L * ke.KVH * (ke.D >> 3);
+    long long gx = (total + 255) / 256;
+    if (gx > 148 * 8) gx = 148 * 8;
+    RTK_LAUNCH_PDL(pivot_keys_compact_kernel, dim3((unsigned)gx, (unsigned)n), 256, 0, st, ke);
+    for (int i = 0; i < n; ++i) {
+        sb.kc[i] = ke.kc[i];
+        sb.slot[i] = ke.slot[i];
+    }
+    sb.n_keys = ke.n_keys;
+    return 0;
+}
+
+static size_t key_elide_bytes(int64_t KVH, int64_t L, int64_t D) {      // per layer: compact K copy + slots, 256-byte granules
+    return (((size_t)KVH * L * D * 2 + 255) & ~(size_t)255) + (((size_t)L * 4 + 255) & ~(size_t)255);
+}
+
 // ======================================================================================== B2: select
 constexpr int kSelThreads = 1024;
 
@@ -659,6 +749,14 @@ kv_block_copy_kernel(CopyJobs j) {
 }
 
 long long g_launches = 0;
+// RTK_NO_KEY_ELISION=1: score key patches like every other key (A/B and debugging; the kept indices do not change)
+bool key_elision_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("RTK_NO_KEY_ELISION");
+        return !(e && e[0] == '1');
+    }();
+    return on;
+}
 bool pdl_enabled() {
     static const bool on = [] {
         const char* e = getenv("RTK_NO_PDL");
@@ -826,7 +924,7 @@ static size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 extern "C" size_t rtk_pivot_update_workspace_bytes(int64_t H, int64_t KVH, int64_t L, int64_t D) {
     if (H < 1 || KVH < 1 || L < 1 || D < 1) return 0;
     return align256(rtk_pivot_score_workspace_bytes(H, L)) + align256((size_t)H * L * D * 2) + align256((size_t)KVH * L * D * 2) +
-           4 * align256((size_t)L * D * 2) + 256;
+           4 * align256((size_t)L * D * 2) + 256 + key_elide_bytes(KVH, L, D) + 256;
 }
 
 extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
@@ -844,7 +942,10 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
     void* sin1 = ws;                    ws += align256((size_t)L * D * 2);
     void* cos2 = ws;                    ws += align256((size_t)L * D * 2);
     void* sin2 = ws;                    ws += align256((size_t)L * D * 2);
-    long long* tmin = (long long*)ws;   // smallest kept temporal position (select -> fused compaction)
+    long long* tmin = (long long*)ws;    ws += 256;   // smallest kept temporal position (select -> fused compaction)
+    char* kc_ws = ws;                    ws += align256((size_t)KVH * L * D * 2);      // key elision: compact K copy,
+    int32_t* slot_ws = (int32_t*)ws;     ws += align256((size_t)L * 4);                //   slots,
+    int32_t* nkeys_ws = (int32_t*)ws;                                                   //   count
     (void)cos2; (void)sin2;
     const void* q = a->q;
     const void* k = a->k;
@@ -899,8 +1000,22 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
         q = qu; k = ku; qsh = ksh = L * D; qsl = ksl = D;
     }
     if (!a->skip_score) {
+        ScoreBatch sb = {};
+        sb.n = 1; sb.H = H; sb.KVH = KVH; sb.L = L; sb.D = D;
+        sb.q[0] = q; sb.k[0] = k; sb.head_scores[0] = a->head_scores;
+        sb.q_stride_h[0] = qsh; sb.q_stride_l[0] = qsl; sb.k_stride_h[0] = ksh; sb.k_stride_l[0] = ksl;
+        if (a->keymask && key_elision_enabled()) {
+            // key patches keep score 1.0 whatever their column sum is: pass 2 only visits the other keys
+            if ((ksh | ksl) % 8 != 0 || D % 8 != 0 || ((uintptr_t)k & 15u) != 0) return RTK_E_ALIGN;
+            KeyElide ke = {};
+            ke.L = (int)L; ke.KVH = (int)KVH; ke.D = (int)D;
+            ke.keymask[0] = a->keymask; ke.slot[0] = slot_ws; ke.k[0] = (const __nv_bfloat16*)k;
+            ke.k_stride_h[0] = ksh; ke.k_stride_l[0] = ksl; ke.kc[0] = (__nv_bfloat16*)kc_ws; ke.n_keys = nkeys_ws;
+            rc = key_elide_prepare(ke, 1, sb, (cudaStream_t)stream);
+            if (rc) return rc;
+        }
         if (a->ev_score_begin) cudaEventRecord((cudaEvent_t)a->ev_score_begin, (cudaStream_t)stream);
-        rc = rtk_pivot_score(q, H, qsh, qsl, k, KVH, ksh, ksl, L, D, a->head_scores, score_ws, rtk_pivot_score_workspace_bytes(H, L), stream);
+        rc = pivot_score_batch(sb, score_ws, rtk_pivot_score_workspace_bytes(H, L), (cudaStream_t)stream);
         if (rc) return rc;
         if (a->ev_score_end) cudaEventRecord((cudaEvent_t)a->ev_score_end, (cudaStream_t)stream);
     }
@@ -961,7 +1076,8 @@ extern "C" size_t rtk_pivot_update_batch_workspace_bytes(int64_t H, int64_t KVH,
     if (H < 1 || KVH < 1 || L < 1 || D < 1 || n_layers < 1) return 0;
     const size_t n = (size_t)(n_layers < kMaxBatchLayers ? n_layers : kMaxBatchLayers);
     return align256(rtk_pivot_score_workspace_bytes(H * (int64_t)n, L)) +
-           n * (align256((size_t)H * L * D * 2) + align256((size_t)KVH * L * D * 2)) + align256(n * sizeof(long long)) + 256;
+           n * (align256((size_t)H * L * D * 2) + align256((size_t)KVH * L * D * 2)) + align256(n * sizeof(long long)) + 256 +
+           n * key_elide_bytes(KVH, L, D) + 256;
 }
 
 #ifndef RTK_UNROT_TOKEN_MAJOR
@@ -981,7 +1097,10 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
     void* score_ws = ws;                ws += align256(rtk_pivot_score_workspace_bytes(H * n, L));
     char* qu0 = ws;                     ws += (size_t)n * align256((size_t)H * L * D * 2);
     char* ku0 = ws;                     ws += (size_t)n * align256((size_t)KVH * L * D * 2);
-    long long* tmin = (long long*)ws;
+    long long* tmin = (long long*)ws;   ws += align256((size_t)n * sizeof(long long)) + 256;
+    char* kc0 = ws;                     ws += (size_t)n * align256((size_t)KVH * L * D * 2);      // key elision: compact K copies,
+    char* slot0 = ws;                   ws += (size_t)n * align256((size_t)L * 4);                //   slots,
+    int32_t* nkeys_ws = (int32_t*)ws;                                                              //   counts
 
     BatchLayers t = {};
     ScoreBatch sb = {};
@@ -1030,6 +1149,22 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
                            a0.attention_scaling, rp);
     }
     if (!a0.skip_score) {
+        bool any_mask = false;
+        for (int i = 0; i < n; ++i) any_mask = any_mask || a[i].keymask != nullptr;
+        if (any_mask && key_elision_enabled()) {
+            // key patches keep score 1.0 whatever their column sum is: pass 2 only visits the other keys of every layer
+            KeyElide ke = {};
+            ke.L = (int)L; ke.KVH = (int)KVH; ke.D = (int)D; ke.n_keys = nkeys_ws;
+            for (int i = 0; i < kMaxBatchLayers; ++i) {
+                const int j = i < n ? i : 0;
+                ke.keymask[i] = a[j].keymask;
+                ke.slot[i] = (int32_t*)(slot0 + (size_t)j * align256((size_t)L * 4));
+                ke.k[i] = t.k[j]; ke.k_stride_h[i] = t.k_stride_h[j]; ke.k_stride_l[i] = t.k_stride_l[j];
+                ke.kc[i] = (__nv_bfloat16*)(kc0 + (size_t)j * align256((size_t)KVH * L * D * 2));
+            }
+            int rc = key_elide_prepare(ke, n, sb, st);
+            if (rc) return rc;
+        }
         if (a0.ev_score_begin) cudaEventRecord((cudaEvent_t)a0.ev_score_begin, st);
         int rc = pivot_score_batch(sb, score_ws, rtk_pivot_score_workspace_bytes(H * n, L), st);
         if (rc) return rc;

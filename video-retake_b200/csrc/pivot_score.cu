@@ -134,6 +134,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(kTi
 template <int NL>
 struct ScoreMaps {
     CUtensorMap q[NL], k[NL];
+    CUtensorMap kc[NL];               // key elision: the compact copy of the keys that are not key patches (pass 2 only)
 };
 
 struct ScoreParams {
@@ -142,6 +143,8 @@ struct ScoreParams {
     int n_atoms;                      // D / 64
     int q_dim1_is_l, k_dim1_is_l;     // tensor-map coordinate order (dims are sorted by stride on the host)
     float inv_sqrt_d;                 // fp32(1 / fp32(sqrt D))
+    const int32_t* n_keys;            // key elision: rows of the compact key copy per layer (device); nullptr = every key
+    int kc_dim1_is_l;
     float2* ml_part;                  // [3][H][nt*128]  pass 1 partials (row max in scaled-logit domain, row sum): a unit is
                                       //                 shared by at most three CTAs - first / middle / last part
     float* stats;                     // [H][nt*128]     c_q = m*log2e + log2(l)   (merge kernel output, pass 2 input)
@@ -259,36 +262,49 @@ __device__ __forceinline__ void softmax_cols(uint32_t (&r)[64], int valid, Softm
 // range of every layer in turn - the cut points inside a layer are those of a single-layer launch, so batched and
 // per-layer scoring fold their fp32 partials in the same order and agree bit for bit.
 struct TileRange {
-    long long g, g1, Gl;
-    int nt, layer, n_layers, units_per_layer;
+    // 32-bit arithmetic: Gl = heads per layer x units per head x streamed tiles <= 256 * 64 * 128 = 2^21 for L <= 16384, and
+    // Gl * (grid + 2) stays below 2^31 (checked on the host)
+    int g, g1, Gl;
+    int nt;                           // streamed tiles of a unit
+    int nt_a, nta;                    // stationary tiles / units per head of the current layer
+    int layer, n_layers, Hl, geff;
+    const int32_t* n_keys;            // pass 2 with key elision: stationary rows per layer
     __device__ __forceinline__ void set_layer_range() {
-        g = Gl * blockIdx.x / gridDim.x;
-        g1 = Gl * (blockIdx.x + 1) / gridDim.x;
+        nt_a = n_keys ? (n_keys[layer] + kTile - 1) / kTile : nt;
+        nta = (nt_a + kPair - 1) / kPair;
+        Gl = Hl * nta * nt;
+        // CTAs that share the layer: all of them unless that would make a range shorter than half a unit (the host sizes the
+        // grid for the full key count; with most keys elided fewer CTAs take part)
+        int ge = Gl / ((nt + 1) / 2);
+        ge = ge < 1 ? 1 : (ge > (int)gridDim.x ? (int)gridDim.x : ge);
+        geff = ge;
+        if ((int)blockIdx.x < geff) {
+            g = (int)((unsigned)Gl * blockIdx.x / (unsigned)geff);
+            g1 = (int)((unsigned)Gl * (blockIdx.x + 1) / (unsigned)geff);
+        } else {
+            g = g1 = 0;
+        }
     }
-    // does the NEXT CTA's range of the current layer reach the end of unit `u` (then the unit has no middle part)?
-    __device__ __forceinline__ bool next_cta_reaches_end_of(int u) const {
-        const int ul = u - layer * units_per_layer;
-        return Gl * (blockIdx.x + 2) / gridDim.x >= (long long)(ul + 1) * nt;
+    // does the NEXT CTA's range of the current layer reach the end of unit `ul` (then the unit has no middle part)?
+    __device__ __forceinline__ bool next_cta_reaches_end_of(int ul) const {
+        return (int)((unsigned)Gl * (blockIdx.x + 2) / (unsigned)geff) >= (ul + 1) * nt;
     }
-    // H: heads of all layers, Hl: heads per layer; a head has ceil(nt / kPair) units of kPair stationary tiles
-    __device__ __forceinline__ TileRange(int H, int Hl, int nt_) : nt(nt_), layer(0) {
-        n_layers = H / Hl;
-        units_per_layer = Hl * ((nt_ + kPair - 1) / kPair);
-        Gl = (long long)units_per_layer * nt_;
+    // H: heads of all layers, Hl: heads per layer; a head has ceil(nt_a / kPair) units of kPair stationary tiles
+    __device__ __forceinline__ TileRange(int H, int Hl_, int nt_, const int32_t* n_keys_) : nt(nt_), layer(0), Hl(Hl_), n_keys(n_keys_) {
+        n_layers = H / Hl_;
         set_layer_range();
     }
-    // u: unit index over all layers (= head-of-all-layers * units per head + stationary tile pair)
-    __device__ __forceinline__ bool next(int& u, int& tb0, int& tb1) {
+    // ul: unit index inside the current layer (= head-of-layer * nta + stationary tile pair); the layer is `layer`
+    __device__ __forceinline__ bool next(int& ul, int& tb0, int& tb1) {
         while (g >= g1) {
             if (++layer >= n_layers) return false;
             set_layer_range();
         }
-        const int ul = (int)(g / nt);
-        tb0 = (int)(g - (long long)ul * nt);
-        const long long left = g1 - g;
-        tb1 = (left < nt - tb0) ? tb0 + (int)left : nt;
+        ul = g / nt;
+        tb0 = g - ul * nt;
+        const int left = g1 - g;
+        tb1 = (left < nt - tb0) ? tb0 + left : nt;
         g += tb1 - tb0;
-        u = layer * units_per_layer + ul;
         return true;
     }
 };
@@ -334,22 +350,24 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
     const int nt = prm.nt;
     const size_t hl = (size_t)prm.H * nt * kTile;            // elements of one [H][Lpad] plane
     // the stationary operand is Q in pass 1 and K in pass 2
-    const CUtensorMap* a_maps = (PASS == 1) ? maps.q : maps.k;
+    // (pass 2 with key elision: the stationary rows are the compact copy of the keys that are not key patches)
+    const bool elide = (PASS == 2) && prm.n_keys != nullptr;
+    const CUtensorMap* a_maps = (PASS == 1) ? maps.q : (elide ? maps.kc : maps.k);
     const CUtensorMap* b_maps = (PASS == 1) ? maps.k : maps.q;
-    const int a_l1 = (PASS == 1) ? prm.q_dim1_is_l : prm.k_dim1_is_l;
+    const int a_l1 = (PASS == 1) ? prm.q_dim1_is_l : (elide ? prm.kc_dim1_is_l : prm.k_dim1_is_l);
     const int b_l1 = (PASS == 1) ? prm.k_dim1_is_l : prm.q_dim1_is_l;
-    TileRange range(prm.H, prm.Hl, nt);
-    int u, tb0, tb1;
-    const int nta = (nt + kPair - 1) / kPair;                // units per head
+    TileRange range(prm.H, prm.Hl, nt, elide ? prm.n_keys : nullptr);
+    int ul, tb0, tb1;
 
     if (warp == 0) {
         // ===================================================================== TMA producer
         if (lane == 0) {
             uint32_t cnt = 0, ucnt = 0;
-            while (range.next(u, tb0, tb1)) {
-                const int hh = u / nta, ta = (u - hh * nta) * kPair; // hh: head index over all layers of the launch; first stationary tile
-                const int layer = (NL == 1) ? 0 : hh / prm.Hl;
-                const int h = hh - layer * prm.Hl;
+            while (range.next(ul, tb0, tb1)) {
+                const int layer = range.layer;
+                const int h = ul / range.nta, ta = (ul - h * range.nta) * kPair;      // head of the layer; first stationary tile
+                const int hh = layer * prm.Hl + h;                                      // head index over all layers of the launch
+                const int nt_a = range.nt_a;
                 const CUtensorMap* a_map = a_maps + layer;
                 const CUtensorMap* b_map = b_maps + layer;
                 const int a_head = (PASS == 1) ? h : h / prm.G;
@@ -363,7 +381,7 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                     for (int kk = 0; kk < prm.n_atoms; ++kk) {
                         // (an odd tile count leaves the last unit one tile short: its second slot repeats the first, the
                         //  softmax side drops that result)
-                        const int row = ((ta + pa < nt) ? ta + pa : ta) * kTile;
+                        const int row = ((ta + pa < nt_a) ? ta + pa : ta) * kTile;
                         tma_load_3d(base + ScoreSmem::a_tile + (as * kPair + pa) * kTileBytes + kk * kHalfBytes, a_map, kk * 64,
                                     a_l1 ? row : a_head, a_l1 ? a_head : row, a_full(as));
                     }
@@ -392,7 +410,7 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
     } else if (warp == 1) {
         // ======================================================================= MMA issuer
         uint32_t cnt = 0, ucnt = 0;
-        while (range.next(u, tb0, tb1)) {
+        while (range.next(ul, tb0, tb1)) {
             const int as = ucnt % kASlots;
             mbar_wait_feeder(a_full(as), (ucnt / kASlots) & 1u);
             ++ucnt;
@@ -436,9 +454,10 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
         const float inv = prm.inv_sqrt_d;
         const uint64_t inv2 = pk2(inv, inv), l2e2 = pk2(kLog2e, kLog2e);
         uint32_t cnt = 0;
-        while (range.next(u, tb0, tb1)) {
-            const int h = u / nta, ta = (u - h * nta) * 2 + (grp >> 1);
-            const bool has_tile = ta < nt;           // odd tile count: the last unit's second tile is a repeat, dropped below
+        while (range.next(ul, tb0, tb1)) {
+            const int hl_ = ul / range.nta, ta = (ul - hl_ * range.nta) * 2 + (grp >> 1);
+            const int h = range.layer * prm.Hl + hl_;          // head index over all layers of the launch
+            const bool has_tile = ta < range.nt_a;   // odd tile count: the last unit's second tile is a repeat, dropped below
             SoftmaxState st;
             for (int tb = tb0; tb < tb1; ++tb, ++cnt) {
                 const int b = 2 * (int)(cnt & 1u) + (grp >> 1);
@@ -466,7 +485,7 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
             // The CTA with the first tiles also writes the neutral element into the planes nobody else will write.
             const bool first = (tb0 == 0), last = (tb1 == nt);
             const int part = first ? 0 : (last ? 2 : 1);
-            const bool fill1 = first && (last || range.next_cta_reaches_end_of(u)), fill2 = first && last;
+            const bool fill1 = first && (last || range.next_cta_reaches_end_of(ul)), fill2 = first && last;
             const size_t o = (size_t)h * nt * kTile + (size_t)ta * kTile + row;
             const int g_lo = grp & ~1;               // the two groups of this stationary tile
             const bool folder = (grp == g_lo) && has_tile;
@@ -525,6 +544,7 @@ __global__ void pivot_stats_merge_kernel(const float2* __restrict__ ml_part, int
 // blockIdx.y runs over the KV heads of all layers of the launch; every layer has its own [KVH, L] output.
 struct HeadScoreOut {
     __nv_bfloat16* p[kMaxBatchLayers];
+    const int32_t* slot[kMaxBatchLayers];   // key elision: column of key k in the partial planes, -1 = key patch (score 1.0); or nullptr
     int KVH;                          // KV heads per layer
 };
 
@@ -535,13 +555,21 @@ __global__ void pivot_head_reduce_kernel(const float* __restrict__ colsum_part, 
     const int g = blockIdx.y;
     if (k >= L) return;
     const size_t hl = (size_t)H * Lpad;
+    const int layer = g / out.KVH;
+    int col = k;
+    if (out.slot[layer]) {
+        col = out.slot[layer][k];
+        if (col < 0) {                // a key patch: its score is 1.0 by definition (longvideo_cache.py:272-274), pass 2 skipped it
+            out.p[layer][(size_t)(g - layer * out.KVH) * L + k] = __float2bfloat16_rn(1.0f);
+            return;
+        }
+    }
     float v[4] = {0.f, 0.f, 0.f, 0.f};
     for (int j = 0; j < G; ++j) {
-        const size_t o = (size_t)(g * G + j) * Lpad + k;
+        const size_t o = (size_t)(g * G + j) * Lpad + col;
         v[j & 3] += round_bf16((colsum_part[o] + colsum_part[hl + o]) + colsum_part[2 * hl + o]);
     }
     const float s = ((v[0] + v[1]) + v[2]) + v[3];
-    const int layer = g / out.KVH;
     out.p[layer][(size_t)(g - layer * out.KVH) * L + k] = __float2bfloat16_rn(s * (1.0f / (float)G));
 }
 
@@ -604,8 +632,16 @@ static int score_launch(const ScoreBatch& b, ScoreParams prm, cudaStream_t st) {
         if (rc) return rc;
         if (l == 0) { prm.q_dim1_is_l = ql; prm.k_dim1_is_l = kl; }
         else if (ql != prm.q_dim1_is_l || kl != prm.k_dim1_is_l) return RTK_E_UNSUPPORTED;   // layers must share a layout
+        if (prm.n_keys) {
+            int cl = 0;                                             // compact key copy: token-major [rows, KVH, D]
+            rc = make_map(&maps.kc[l], b.kc[l], b.KVH, b.L, b.D, b.D, b.KVH * b.D, &cl);
+            if (rc) return rc;
+            prm.kc_dim1_is_l = cl;
+        } else {
+            maps.kc[l] = maps.k[l];
+        }
     }
-    for (int l = b.n; l < NL; ++l) { maps.q[l] = maps.q[0]; maps.k[l] = maps.k[0]; }
+    for (int l = b.n; l < NL; ++l) { maps.q[l] = maps.q[0]; maps.k[l] = maps.k[0]; maps.kc[l] = maps.kc[0]; }
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -620,7 +656,10 @@ static int score_launch(const ScoreBatch& b, ScoreParams prm, cudaStream_t st) {
     if (e != cudaSuccess) return (int)e;
     HeadScoreOut out;
     out.KVH = (int)b.KVH;
-    for (int l = 0; l < kMaxBatchLayers; ++l) out.p[l] = reinterpret_cast<__nv_bfloat16*>(b.head_scores[l < b.n ? l : 0]);
+    for (int l = 0; l < kMaxBatchLayers; ++l) {
+        out.p[l] = reinterpret_cast<__nv_bfloat16*>(b.head_scores[l < b.n ? l : 0]);
+        out.slot[l] = prm.n_keys ? b.slot[l < b.n ? l : 0] : nullptr;
+    }
     RTK_LAUNCH_PDL((pivot_score_kernel<1, NL>), grid, kScoreThreads2, smem, st, maps, prm);
     dim3 g1((unsigned)((prm.nt * kTile + 255) / 256), (unsigned)prm.H);
     RTK_LAUNCH_PDL(pivot_stats_merge_kernel, g1, 256, 0, st, prm.ml_part, prm.H, prm.L, prm.nt * kTile, prm.stats);
@@ -633,7 +672,7 @@ static int score_launch(const ScoreBatch& b, ScoreParams prm, cudaStream_t st) {
 // scoring of b.n layers of one chunk (same H, KVH, L, D) by one chain of four launches
 int pivot_score_batch(const ScoreBatch& b, void* workspace, size_t workspace_bytes, cudaStream_t st) {
     if (b.n < 1 || b.n > kMaxBatchLayers || !workspace || b.H < 1 || b.KVH < 1 || b.L < 1) return RTK_E_BADARG;
-    if ((b.D != 64 && b.D != 128) || b.H % b.KVH != 0 || b.L > 16384) return RTK_E_UNSUPPORTED;
+    if ((b.D != 64 && b.D != 128) || b.H % b.KVH != 0 || b.L > 16384 || b.H > 256) return RTK_E_UNSUPPORTED;   // (TileRange: 32-bit)
     if (((uintptr_t)workspace & 15u) != 0) return RTK_E_ALIGN;
     for (int l = 0; l < b.n; ++l) {
         if (!b.q[l] || !b.k[l] || !b.head_scores[l]) return RTK_E_BADARG;
@@ -649,7 +688,11 @@ int pivot_score_batch(const ScoreBatch& b, void* workspace, size_t workspace_byt
     prm.L = (int)b.L;
     prm.nt = (int)((b.L + kTile - 1) / kTile);
     prm.n_atoms = (int)(b.D / 64);
-    prm.q_dim1_is_l = prm.k_dim1_is_l = 0;
+    prm.q_dim1_is_l = prm.k_dim1_is_l = prm.kc_dim1_is_l = 0;
+    prm.n_keys = b.n_keys;
+    if (b.n_keys)
+        for (int l = 0; l < b.n; ++l)
+            if (!b.kc[l] || !b.slot[l] || ((uintptr_t)b.kc[l] & 15u) != 0) return RTK_E_BADARG;
     const float sq = (float)sqrt((double)b.D);
     prm.inv_sqrt_d = 1.0f / sq;
     const size_t plane = (size_t)prm.H * prm.nt * kTile;

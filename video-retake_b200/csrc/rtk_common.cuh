@@ -51,6 +51,13 @@ struct ScoreBatch {
     const void* k[kMaxBatchLayers];                  // bf16 [KVH, L, D] views
     void* head_scores[kMaxBatchLayers];              // bf16 [KVH, L] each
     int64_t q_stride_h[kMaxBatchLayers], q_stride_l[kMaxBatchLayers], k_stride_h[kMaxBatchLayers], k_stride_l[kMaxBatchLayers];
+    // Key elision (optional, all three set or none): key-patch tokens get score 1.0 whatever their column sum is
+    // (longvideo_cache.py:272-274), so pass 2 only visits the other keys.  kc[l]: bf16 [n_keys[l], KVH, D] token-major copy of
+    // the rows of k[l] that are NOT key patches, in order; slot[l][j]: row of key j in kc[l], -1 for a key patch;
+    // n_keys: device array [n].  head_scores of key patches are written as 1.0.
+    const void* kc[kMaxBatchLayers];
+    const int32_t* slot[kMaxBatchLayers];
+    const int32_t* n_keys;
 };
 int pivot_score_batch(const ScoreBatch& b, void* workspace, size_t workspace_bytes, cudaStream_t st);
 
