@@ -704,6 +704,32 @@ def main():
         immediate = {"value": world * s.frames / (ims / a.steps * 1e-3), "unit": UNIT, "ms_per_step": ims / a.steps,
                      "what": "deferred_compression off: compression inside every update(), bit-identical results"}
 
+    # ---- A/B inside the same process: key elision off (pass 2 of the scoring visits every key, like round 1); the kept
+    #      indices are the same, only the time differs - reported next to `value`, never instead of it
+    no_elision = None
+    if not a.no_immediate_ab:
+        lib_ = _native.lib()
+        prev = lib_.rtk_debug_key_elision(0)
+        try:
+            run_step(s, x, q, k, v, rotary, lc, vc, pos_grid)
+            sync_all()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0.record()
+            for _ in range(a.steps):
+                run_step(s, x, q, k, v, rotary, lc, vc, pos_grid)
+            n1.record()
+            sync_all()
+        finally:
+            lib_.rtk_debug_key_elision(prev)
+        nms = n0.elapsed_time(n1)
+        if dist is not None:
+            t = torch.tensor([nms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            nms = float(t)
+        no_elision = {"value": world * s.frames / (nms / a.steps * 1e-3), "unit": UNIT, "ms_per_step": nms / a.steps,
+                      "what": "rtk_debug_key_elision(0): pass 2 of the scoring also visits the key patches (whose score the "
+                              "reference overwrites with 1.0 before the top-k); same kept indices"}
+
     # ---- end to end: inputs in pinned host memory, H2D + D2H inside the timed region
     e2e = None
     if not a.no_e2e:
@@ -774,7 +800,7 @@ def main():
     score_ms = timer.mean_ms()
     flops = 2.0 * s.H * s.L * s.L * s.D
     achieved = flops / (score_ms * 1e-3) / 1e12 if score_ms > 0 else 0.0
-    elide = os.environ.get("RTK_NO_KEY_ELISION") != "1"
+    elide = bool(_native.lib().rtk_debug_key_elision(-1))
     executed = 2.0 - (key_patch_share if (elide and key_patch_share is not None) else 0.0)
     roofline = {"kernel": ("pivot_score_kernel<1> + pivot_score_kernel<2> (the scoring of one layer; timed around the batched "
                            f"scoring of a chunk's {s.layers} layers, divided by {s.layers})") if s.deferred else
@@ -823,6 +849,8 @@ def main():
         line["sharded_within_video"] = sharded
     if immediate is not None:
         line["immediate_compression"] = immediate
+    if no_elision is not None:
+        line["no_key_elision"] = no_elision
     if e2e is not None:
         line["e2e"] = e2e
     if clocks is not None:

@@ -46,6 +46,11 @@ int         rtk_version(void);
  * the sources lying next to it, so a record always says which sources ran. */
 const char* rtk_build_id(void);
 const char* rtk_error_string(int code);
+/* A/B and debugging: pass 2 of the PivotKV scoring skips the key-patch tokens (their score is overwritten with 1.0 before
+ * the top-k, longvideo_cache.py:272-274; rtk_pivot_update / _batch with a keymask).  on = 0 / 1 switches that off / on for the
+ * process (the RTK_NO_KEY_ELISION=1 environment variable sets the initial state), on < 0 only queries; returns the previous
+ * state.  The kept indices are the same either way. */
+int         rtk_debug_key_elision(int on);
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t     rtk_launch_count(void);
 

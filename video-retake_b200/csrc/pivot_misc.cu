@@ -749,13 +749,15 @@ kv_block_copy_kernel(CopyJobs j) {
 }
 
 long long g_launches = 0;
-// RTK_NO_KEY_ELISION=1: score key patches like every other key (A/B and debugging; the kept indices do not change)
+// RTK_NO_KEY_ELISION=1 (or rtk_debug_key_elision(0)): score key patches like every other key - for A/B runs and debugging;
+// the kept indices do not change
+static int g_key_elision = -1;
 bool key_elision_enabled() {
-    static const bool on = [] {
+    if (g_key_elision < 0) {
         const char* e = getenv("RTK_NO_KEY_ELISION");
-        return !(e && e[0] == '1');
-    }();
-    return on;
+        g_key_elision = (e && e[0] == '1') ? 0 : 1;
+    }
+    return g_key_elision != 0;
 }
 bool pdl_enabled() {
     static const bool on = [] {
@@ -770,6 +772,12 @@ bool pdl_enabled() {
 using namespace rtk;
 
 extern "C" int rtk_version(void) { return RTK_ABI_VERSION; }
+
+extern "C" int rtk_debug_key_elision(int on) {
+    const int prev = rtk::key_elision_enabled() ? 1 : 0;
+    if (on >= 0) rtk::g_key_elision = on ? 1 : 0;
+    return prev;
+}
 
 #ifndef RTK_BUILD_ID
 #define RTK_BUILD_ID "unknown"

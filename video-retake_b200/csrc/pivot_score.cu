@@ -466,7 +466,7 @@ pivot_score_kernel(const __grid_constant__ ScoreMaps<NL> maps, ScoreParams prm) 
                 if (PASS == 2) mbar_wait(st_full(cnt % kStatSlots), (cnt / kStatSlots) & 1u);
                 const int valid = prm.L - tb * kTile - half * 64;      // streamed rows of this half that exist
                 const float* cq = reinterpret_cast<const float*>(smem + ScoreSmem::stats) + (cnt % kStatSlots) * kTile + half * 64;
-                {
+                if (has_tile) {              // (the spare slot of an odd tile count holds a repeat: nothing to read there)
                     uint32_t r[64];
                     tmem_ld64(lane_addr + b * kTile, r);
                     tmem_ld_wait();

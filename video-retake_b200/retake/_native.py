@@ -35,6 +35,7 @@ def lib() -> C.CDLL:
     sig = {
         "rtk_version": ([], C.c_int),
         "rtk_build_id": ([], C.c_char_p),
+        "rtk_debug_key_elision": ([i32], C.c_int),
         "rtk_error_string": ([C.c_int], C.c_char_p),
         "rtk_launch_count": ([], i64),
         "rtk_dpselect_dis": ([p, i64, i64, i64, i32, p, p], C.c_int),
@@ -96,7 +97,7 @@ def build_id() -> str:
     return lib().rtk_build_id().decode()
 
 
-EXPORTS = ("rtk_version", "rtk_build_id", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
+EXPORTS = ("rtk_version", "rtk_build_id", "rtk_debug_key_elision", "rtk_error_string", "rtk_launch_count", "rtk_dpselect_dis", "rtk_dpselect_select",
            "rtk_dpselect_gather", "rtk_dpselect_keyframe", "rtk_gather_rows", "rtk_dpselect_gather_owned", "rtk_mallm_workspace_bytes", "rtk_mallm_compress", "rtk_pivot_rope", "rtk_pivot_score_workspace_bytes", "rtk_pivot_score",
            "rtk_pivot_select", "rtk_pivot_compact", "rtk_pivot_rope_tables", "rtk_pivot_update_workspace_bytes",
            "rtk_pivot_update", "rtk_pivot_update_batch_workspace_bytes", "rtk_pivot_update_batch", "rtk_kv_block_copy")
