@@ -82,7 +82,9 @@ def _worker(rank, world, port):
                                              per, mask, pos.clone(), rot, mrope, reforge, **extra)
                     # per-head rows: last-bit differences against the full-width launch are possible (fp32 fold order of a
                     # unit split between CTAs); the kept set is the single-GPU one or differs on the cut
-                    d = (hs.view(torch.int16).int() - cache.last_head_scores.view(torch.int16).int()).abs()
+                    # (key-patch columns are left out: the fused paths write the reference's 1.0 there without computing
+                    # them, the unfused rtk_pivot_score computes every column - section 4 "key elision")
+                    d = (hs.view(torch.int16).int() - cache.last_head_scores.view(torch.int16).int()).abs()[:, ~mask]
                     assert int(d.max()) <= 1 and float((d > 0).float().mean()) < 1e-3, (transport, rep)
                     from helpers import index_parity
                     full_score = cache.last_head_scores.float().mean(0).to(torch.bfloat16).masked_fill(mask, 1.0)

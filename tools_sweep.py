@@ -40,7 +40,7 @@ name = "sweep_n%d%s.jsonl" % (gpus, "_llava" if arg("--llava") else "")
 with open(os.path.join(ROOT, "gpurun_out", name), "w") as out:
     for i, (shape, frames, rv, rkv) in enumerate(points):
         bench = [os.path.join(ROOT, "bench.py"), "--gpus", str(gpus), "--shape", shape, "--frames", str(frames), "--visual-ratio", str(rv),
-                 "--kv-ratio", str(rkv), "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--no-immediate-ab", "--no-sharded",
+                 "--kv-ratio", str(rkv), "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-immediate-ab", "--no-sharded",
                  "--no-parity"]
         if gpus > 1:
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(gpus), "--master-addr",
