@@ -39,8 +39,12 @@ os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 name = "sweep_n%d%s.jsonl" % (gpus, "_llava" if arg("--llava") else "")
 with open(os.path.join(ROOT, "gpurun_out", name), "w") as out:
     for i, (shape, frames, rv, rkv) in enumerate(points):
+        # enough steps for ~1 s of timed work: the first step after the synchronisation pays the clock ramp of an idle GPU
+        # and the host's launch latency (several ms), which a two-step run of a short video would not amortise
+        est_ms = frames * rv * (0.30 if shape == "qwen2vl" else 0.65)
+        steps = max(3, min(40, int(1000.0 / est_ms) + 1))
         bench = [os.path.join(ROOT, "bench.py"), "--gpus", str(gpus), "--shape", shape, "--frames", str(frames), "--visual-ratio", str(rv),
-                 "--kv-ratio", str(rkv), "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-immediate-ab", "--no-sharded",
+                 "--kv-ratio", str(rkv), "--steps", str(steps), "--warmup", "3", "--no-cpu-baseline", "--no-immediate-ab", "--no-sharded",
                  "--no-parity"]
         if gpus > 1:
             cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(gpus), "--master-addr",
@@ -54,7 +58,7 @@ with open(os.path.join(ROOT, "gpurun_out", name), "w") as out:
             continue
         d = json.loads(line[-1])
         rec = {"shape": shape, "frames": frames, "n_gpus": gpus, "visual_ratio": rv, "kv_ratio": d["config"]["kv_ratio"],
-               "frames_per_s": d["value"], "ms_per_step": d["ms_per_step"], "score_ms": d["roofline"]["ms_per_call"],
+               "frames_per_s": d["value"], "ms_per_step": d["ms_per_step"], "steps": d["steps"], "score_ms": d["roofline"]["ms_per_call"],
                "score_frac": d["roofline"]["frac"], "dpselect_ms": d["roofline_dpselect"]["ms_per_call"],
                "dpselect_frac": d["roofline_dpselect"]["frac"], "e2e_frames_per_s": (d.get("e2e") or {}).get("value"),
                "clocks": d.get("clocks"), "build_id": d.get("build_id")}

@@ -1,15 +1,20 @@
 """Splitting ONE video across the GPUs of a box.  Whole videos need no code: one process per
 GPU, each running the single-GPU operators (``bench.py --gpus N``; the reference's own pattern, ``infer_eval.py:181``).
 
-Two exchange steps exist inside a video, both tiny all-gathers over NCCL (or gloo in the CPU tests of the host logic):
+Two exchange steps exist inside a video:
 
 * **DPSelect by frame range**: rank r owns frames ``[t0, t1)`` plus the last frame of rank r-1 as a halo, computes its
-  rows of ``dis`` (``rtk_dpselect_dis(halo=1)``), all ranks all-gather ``dis`` (fp32 ``[T, N]``, <= 6 MB) because peaks
-  look one frame across the seam and the top-t is global, run the identical selection, and compact only the survivors
-  they own.  Kept indices are bit-identical on every rank by construction.
-* **PivotKV by KV head**: rank r owns KV heads ``[g0, g1)`` and the query heads of those groups, computes their
-  line-269 score rows (``rtk_pivot_score``), all ranks all-gather the ``[KVH, L]`` bf16 rows (32-50 KB), take the mean
-  over KV heads in the reference's order, select identically, and compact their own heads.
+  rows of ``dis`` (``rtk_dpselect_dis(halo=1)``), all ranks gather ``dis`` (fp32 ``[T, N]``, <= 6 MB; ONE
+  ``all_gather_into_tensor``) because peaks look one frame across the seam and the top-t is global, run the identical
+  selection, and ``rtk_dpselect_gather_owned`` writes the survivors a rank owns straight into their output slots
+  (``dpselect_frame_sharded_fused``; ``dpselect_frame_sharded`` is the round-1 form that returns rows + slot numbers).
+  Kept indices are bit-identical on every rank by construction.
+* **PivotKV by KV head**: rank r owns KV heads ``[g0, g1)`` and the query heads of those groups.  Two C-ABI calls around
+  one exchange of the ``[KVH_local, L]`` bf16 score rows (16-50 KB): ``rtk_pivot_update(skip_select)`` un-rotates and
+  scores the local heads, the rows travel as NVLink peer stores issued by the library's own put kernel (``ScoreExchange``,
+  torch symmetric memory) or as one NCCL ``all_gather_into_tensor``, and ``rtk_pivot_update(skip_score)`` takes the mean
+  over ALL KV heads in the reference's order, selects identically on every rank and compacts the local heads
+  (``pivot_update_kv_sharded``; ``pivot_update_batch_kv_sharded`` does it for all layers of a chunk with one exchange).
 
 The partition / gather helpers are device-agnostic torch code so that they can be tested with gloo on CPU; only the
 functions that take CUDA tensors call into the library.
