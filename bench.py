@@ -663,8 +663,11 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     marks = []
     e0.record()
+    host_s = []
     for _ in range(a.steps):
+        h0 = time.perf_counter()
         res = run_step(s, x, q, k, v, rotary, lc, vc, pos_grid, timer)
+        host_s.append(time.perf_counter() - h0)          # the host's time to ENQUEUE a step (no synchronisation inside)
         marks.append(torch.cuda.Event(enable_timing=True))
         marks[-1].record()
     e1.record()
@@ -843,7 +846,10 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": config, "roofline": roofline, "roofline_dpselect": dpselect_roofline,
             "gpu_launches": int(launches),
-            "step_ms": {"median": sorted(per_step)[len(per_step) // 2], "min": min(per_step), "max": max(per_step)}}
+            "step_ms": {"median": sorted(per_step)[len(per_step) // 2], "min": min(per_step), "max": max(per_step),
+                        # host time to enqueue one step (first step, GPU idle, and the median of the rest): when it approaches
+                        # the device time the step is bound by the Python host, not by the kernels
+                        "host_enqueue_first": host_s[0] * 1e3, "host_enqueue_median": sorted(host_s)[len(host_s) // 2] * 1e3}}
     line["build_id"] = _native.build_id()
     if dps_half is not None:
         hms, hby = dps_half

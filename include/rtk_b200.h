@@ -230,7 +230,9 @@ typedef struct rtk_pivot_update_args {
      * head_scores == (bf16*)xchg_scores[xchg_rank] + xchg_rank * KVH * L, copies those rows into the same rows of every
      * peer's buffer and then stores xchg_epoch into xchg_flags[r][xchg_rank] for every r (release, system scope).  Call 2
      * expects head_scores == xchg_scores[xchg_rank]; its select kernel first waits until all xchg_world words of
-     * xchg_flags[xchg_rank] equal xchg_epoch.  Use two buffer / flag sets alternately (a rank may be one update ahead).     */
+     * xchg_flags[xchg_rank] equal xchg_epoch.  Use two buffer / flag sets alternately (a rank may be one update ahead).
+     * The wait is bounded: after RTK_XCHG_TIMEOUT_S seconds (environment, default 120, 0 = for ever) the kernel traps and
+     * the stream reports a CUDA error - a lost peer must not hang the GPU.                                                 */
     int32_t xchg_world, xchg_rank;
     uint32_t xchg_epoch;
     void* xchg_scores[8];

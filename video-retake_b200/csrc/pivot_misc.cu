@@ -484,6 +484,24 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// threads [0, n) each wait for one rank's flag to show `epoch`.  A peer that never arrives (crashed process, diverged
+// control flow) must not hang the GPU for good: after `timeout_ns` (0 = wait for ever) the launch traps, which the host
+// sees as a CUDA error at its next synchronisation.
+__device__ __forceinline__ void xchg_wait(const uint32_t* flags, int n, uint32_t epoch, unsigned long long timeout_ns) {
+    if ((int)threadIdx.x < n) {
+        const unsigned long long t0 = globaltimer_ns();
+        while (ld_acquire_sys(flags + threadIdx.x) != epoch) {
+            __nanosleep(64);
+            if (timeout_ns && globaltimer_ns() - t0 > timeout_ns) __trap();
+        }
+    }
+    __syncthreads();
+}
 struct XchgPut {
     const __nv_bfloat16* src;        // this rank's rows inside its own buffer
     __nv_bfloat16* dst[8];           // the same rows inside every rank's buffer (dst[rank] == src: skipped)
@@ -554,27 +572,19 @@ __global__ void __launch_bounds__(kSelThreads)
 pivot_select_kernel(const __nv_bfloat16* __restrict__ head_scores, int KVH, int L, const uint8_t* __restrict__ keymask,
                     int keep, int32_t* __restrict__ keep_idx, __nv_bfloat16* __restrict__ score_out,
                     const long long* __restrict__ tpos, long long* __restrict__ tmin_out,
-                    const uint32_t* __restrict__ wait_flags, int wait_n, uint32_t wait_epoch) {
+                    const uint32_t* __restrict__ wait_flags, int wait_n, uint32_t wait_epoch, unsigned long long wait_ns) {
     pdl_enter();
-    if (wait_flags) {
-        // rows of the other ranks arrive over NVLink: nothing of head_scores is read before every rank's flag is up
-        if ((int)threadIdx.x < wait_n)
-            while (ld_acquire_sys(wait_flags + threadIdx.x) != wait_epoch) __nanosleep(64);
-        __syncthreads();
-    }
+    // rows of the other ranks arrive over NVLink: nothing of head_scores is read before every rank's flag is up
+    if (wait_flags) xchg_wait(wait_flags, wait_n, wait_epoch, wait_ns);
     pivot_select_body(head_scores, KVH, L, keymask, keep, keep_idx, score_out, tpos, tmin_out);
 }
 
 // one CTA per layer of the chunk
 __global__ void __launch_bounds__(kSelThreads)
 pivot_select_batch_kernel(const __grid_constant__ BatchLayers t, int KVH, int L, int keep, int reforge, long long* __restrict__ tmin,
-                          const uint32_t* __restrict__ wait_flags, int wait_n, uint32_t wait_epoch) {
+                          const uint32_t* __restrict__ wait_flags, int wait_n, uint32_t wait_epoch, unsigned long long wait_ns) {
     pdl_enter();
-    if (wait_flags) {
-        if ((int)threadIdx.x < wait_n)
-            while (ld_acquire_sys(wait_flags + threadIdx.x) != wait_epoch) __nanosleep(64);
-        __syncthreads();
-    }
+    if (wait_flags) xchg_wait(wait_flags, wait_n, wait_epoch, wait_ns);
     const int layer = blockIdx.x;
     pivot_select_body(t.head_scores[layer], KVH, L, t.keymask[layer], keep, t.keep_idx[layer], nullptr,
                       reforge ? t.pos[layer] : nullptr, reforge ? tmin + layer : nullptr);
@@ -759,6 +769,15 @@ bool key_elision_enabled() {
     }
     return g_key_elision != 0;
 }
+// how long a select kernel waits for its peers' score rows before it traps (RTK_XCHG_TIMEOUT_S, default 120; 0 = for ever)
+unsigned long long xchg_timeout_ns() {
+    static const unsigned long long ns = [] {
+        const char* e = getenv("RTK_XCHG_TIMEOUT_S");
+        const double s = (e && e[0]) ? atof(e) : 120.0;
+        return s > 0.0 ? (unsigned long long)(s * 1e9) : 0ull;
+    }();
+    return ns;
+}
 bool pdl_enabled() {
     static const bool on = [] {
         const char* e = getenv("RTK_NO_PDL");
@@ -838,7 +857,7 @@ extern "C" int rtk_pivot_select(const void* head_scores, int64_t KVH, int64_t L,
     if (e != cudaSuccess) return (int)e;
     RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream, (const __nv_bfloat16*)head_scores, (int)KVH,
                    (int)L, keymask, (int)keep, keep_idx, (__nv_bfloat16*)score_out, (const long long*)nullptr, (long long*)nullptr,
-                   (const uint32_t*)nullptr, 0, 0u);
+                   (const uint32_t*)nullptr, 0, 0u, 0ull);
     return 0;
 }
 
@@ -1051,7 +1070,8 @@ extern "C" int rtk_pivot_update(const rtk_pivot_update_args* a, void* stream) {
         RTK_LAUNCH_PDL(pivot_select_kernel, 1, kSelThreads, smem, (cudaStream_t)stream, (const __nv_bfloat16*)a->head_scores,
                        (int)score_rows, (int)L, a->keymask, (int)a->keep, a->keep_idx, (__nv_bfloat16*)nullptr,
                        (const long long*)(a->reforge ? a->pos : nullptr), a->reforge ? tmin : (long long*)nullptr,
-                       (const uint32_t*)(xchg ? a->xchg_flags[a->xchg_rank] : nullptr), xchg ? a->xchg_world : 0, a->xchg_epoch);
+                       (const uint32_t*)(xchg ? a->xchg_flags[a->xchg_rank] : nullptr), xchg ? a->xchg_world : 0, a->xchg_epoch,
+                       xchg_timeout_ns());
     }
     // K (possibly the un-rotated copy), V (caller's strides), positions and - on the fast path - the forward rotation
     // at the re-indexed positions: one launch, one CTA per kept token
@@ -1202,7 +1222,7 @@ static int pivot_update_group(const rtk_pivot_update_args* a, int n, char* ws, c
         if (e != cudaSuccess) return (int)e;
         RTK_LAUNCH_PDL(pivot_select_batch_kernel, (unsigned)n, kSelThreads, smem, st, t, (int)score_rows, (int)L, (int)a0.keep,
                        reforge ? 1 : 0, tmin, (const uint32_t*)(xchg ? a0.xchg_flags[a0.xchg_rank] : nullptr),
-                       xchg ? a0.xchg_world : 0, a0.xchg_epoch);
+                       xchg ? a0.xchg_world : 0, a0.xchg_epoch, xchg_timeout_ns());
     }
     {
         CompactParams p = {};

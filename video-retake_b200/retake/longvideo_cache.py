@@ -54,7 +54,10 @@ _WS: Dict[Any, torch.Tensor] = {}
 
 
 def _workspace(device, need: int) -> torch.Tensor:
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """scratch of the update calls, one per (device, stream): launches on different streams must not share it, and a
+    buffer that is replaced by a larger one goes back to the allocator on the stream its kernels were queued on"""
+    index = device.index if device.index is not None else torch.cuda.current_device()
+    key = (index, torch.cuda.current_stream(index).cuda_stream)
     ws = _WS.get(key)
     if ws is None or ws.numel() < need:
         ws = torch.empty(need, dtype=torch.uint8, device=device)
@@ -429,8 +432,8 @@ class PivotKVLayer(DynamicLayer):
 
     def lazy_initialization(self, key_states, value_states=None):
         self.dtype, self.device = key_states.dtype, key_states.device
-        self._keys_view = torch.tensor([], dtype=self.dtype, device=self.device)
-        self._values_view = torch.tensor([], dtype=self.dtype, device=self.device)
+        self._keys_view = torch.empty((0,), dtype=self.dtype, device=self.device)
+        self._values_view = torch.empty((0,), dtype=self.dtype, device=self.device)
         self.is_initialized = True
 
     def get_seq_length(self) -> int:
@@ -685,10 +688,12 @@ class PivotKVCache(DynamicCache):
         l's slice is a tensor of its own (it can be handed to ``update`` with ``position_ids_owned``)."""
         prevs = [self.get_prev_temporal_idx(l) for l in range(n_layers)]
         dev = position_ids.device
-        if all(not isinstance(p, torch.Tensor) for p in prevs):
-            prev = torch.tensor([int(p) for p in prevs], dtype=position_ids.dtype, device=dev)
+        # host integers (-1: nothing cached yet) become device values through fill kernels: torch.tensor(list, device=cuda)
+        # is a pageable host-to-device copy, which synchronises the stream - once per video, with the GPU idle behind it
+        if all(not isinstance(p, torch.Tensor) for p in prevs) and len(set(int(p) for p in prevs)) == 1:
+            prev = torch.full((n_layers,), int(prevs[0]), dtype=position_ids.dtype, device=dev)
         else:
-            prev = torch.stack([p if isinstance(p, torch.Tensor) else torch.tensor(int(p), dtype=position_ids.dtype, device=dev)
+            prev = torch.stack([p if isinstance(p, torch.Tensor) else torch.full((), int(p), dtype=position_ids.dtype, device=dev)
                                 for p in prevs])
         out = position_ids.unsqueeze(0).repeat(n_layers, *([1] * position_ids.dim()))
         first = position_ids[0].reshape(-1)[0]
