@@ -274,3 +274,50 @@ def test_deferred_unsupported_shape_takes_the_immediate_path():
     with pytest.raises(Exception):
         cache.update(k, v, 0, {"query_states": q, "position_ids": _positions(128, 0, None)})
     assert not cache._deferred and cache.layers[0]._deferred_owner is None
+
+
+@pytest.mark.parametrize("deferred", [True, False])
+@pytest.mark.parametrize("reforge", [True, False])
+def test_chunk_loop_never_synchronises_the_host(deferred, reforge):
+    """DPSelect, the re-based ids of a new chunk, every update() and the batched flush only ENQUEUE work: with
+    torch's sync debug mode on "error" any blocking call (``.item()``, a pageable host-to-device copy such as
+    ``torch.tensor(list, device="cuda")``, ``nonzero`` ...) raises.  Round 2 found one such copy per video in
+    ``rebased_position_ids`` - the GPU idled behind it while the host enqueued the first chunk."""
+    lc = _lc()
+    from retake import visual_compression as vc
+    H, KVH, L, D, layers, chunks, ratio, mrope = 8, 2, 256, 64, 3, 3, 0.25, [8, 12, 12]
+    rot = TableRotary(D, mrope=True)
+    rot.inv_freq = rot.inv_freq.cuda()
+    x = torch.randn(12, 64, 256, device="cuda").to(BF)
+    data = [[qkv(H, KVH, L, D, 1.0, seed=7 * c + layer) for layer in range(layers)] for c in range(chunks)]
+    pos_grid = _positions(L, 0, mrope, n_tok=64)
+
+    def one_video():
+        out, mask = vc.memory_bank_compress_keyframe(x[None], 12, 3, sync=False)
+        cfg = _cfg(H, KVH, D, layers, ratio, reforge)
+        cfg.longvideo_kwargs["kvcache_compression_kwargs"]["deferred_compression"] = deferred
+        cache = lc.PivotKVCache(cfg)
+        for c in range(chunks):
+            cache.kvcache_compression = True
+            cache.keypatches_mask_chunk = mask[c * L:(c + 1) * L]
+            pos_all = cache.rebased_position_ids(pos_grid, layers)
+            for layer in range(layers):
+                q, k, v = data[c][layer]
+                cache.update(k, v, layer, {"query_states": q, "position_ids": pos_all[layer], "rotary_emb": rot,
+                                           "mrope_section": mrope, "position_ids_owned": True})
+            cache.after_forward()
+        return cache
+
+    ref = one_video()                                   # warm-up: library load, function attributes, allocator blocks
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        cache = one_video()
+        with pytest.raises(RuntimeError):               # the detector does see the class of call that was removed
+            torch.tensor([1, 2], device="cuda")
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    torch.cuda.synchronize()
+    for layer in range(layers):
+        assert torch.equal(cache.layers[layer].keys, ref.layers[layer].keys)
+        assert cache.get_seq_length(layer) == chunks * int(ratio * L)
