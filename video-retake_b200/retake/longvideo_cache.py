@@ -559,7 +559,7 @@ class PivotKVCache(DynamicCache):
         self.score_events = None            # optional (cudaEvent_t, cudaEvent_t) ints recorded around the next scoring
         # Deferred compression: ``update`` only appends the chunk and remembers its tensors; the
         # compression of ALL layers of the chunk runs as one batched call (``rtk_pivot_update_batch``, seven launches
-        # per chunk instead of eight per layer) when the chunk's forward is over - ``after_forward()``, the hook the
+        # per chunk - nine with a key-patch mask - instead of eight per layer) when the chunk's forward is over - ``after_forward()``, the hook the
         # reference's chunk loop already calls (``qwen2_vl.py:715-716``) - or at the next cache operation that needs
         # the result.  A chunk's kept rows are first read by the NEXT chunk, so the cache contents every reader sees
         # are the same as with compression inside ``update``.  Knob: ``kvcache_compression_kwargs.deferred_compression``
