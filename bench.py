@@ -521,7 +521,7 @@ def cpu_reference_step(s, sample_T, host, it):
     """bounded sample of the reference's CPU path: DPSelect on sample_T grids + ONE compressing update at the real chunk
     length; returns (seconds extrapolated to the whole video - cost is linear in grids and in layer-chunks -, DPSelect
     seconds, update seconds, kind).  kind "reference": the UNMODIFIED reference functions (oracle/real_reference.py finds
-    them in $RETAKE_REFERENCE, baseline/_ref or /root/reference); kind "port": oracle/reference_ops.py, the same torch op
+    them in $RETAKE_REFERENCE or baseline/_ref - never in /root/reference at run time); kind "port": oracle/reference_ops.py, the same torch op
     sequence (bit-identical on CPU, tests/test_oracle_golden.py) when no reference tree is around."""
     from helpers import TableRotary
     from oracle import real_reference

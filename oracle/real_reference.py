@@ -7,6 +7,8 @@ reference tree itself does not), ``/root/reference``.  The two modules import an
 transformers 5.5; ``PivotKVCache.update`` assigns ``self.key_cache[i]`` (transformers 4.48 naming,
 ``longvideo_cache.py:313``), so the class is instantiated through a subclass that only adds list views onto
 ``layers[i].keys / .values`` - the same 10-line shim ``tests/golden/make_golden.py`` pinned the fixtures with.
+``/root/reference`` is only looked at when the caller asks for it (``allow_system_tree=True``: CPU tests in the build
+container); ``bench.py`` and the GPU tests never read it - they use the copy that travelled with the snapshot.
 
 Used by ``bench.py`` (the ``cpu_baseline`` leg and ``--impl reference``: ``kind: "reference"``) and by tests; nothing under
 ``video-retake_b200/`` imports it."""
@@ -16,12 +18,13 @@ import sys
 import types
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CANDIDATES = [os.environ.get("RETAKE_REFERENCE"), os.path.join(ROOT, "baseline", "_ref"), "/root/reference"]
+CANDIDATES = [os.environ.get("RETAKE_REFERENCE"), os.path.join(ROOT, "baseline", "_ref")]
+SYSTEM_TREE = "/root/reference"
 FILES = ("visual_compression.py", "longvideo_cache.py")
 
 
-def find():
-    for c in CANDIDATES:
+def find(allow_system_tree=False):
+    for c in CANDIDATES + ([SYSTEM_TREE] if allow_system_tree else []):
         if c and all(os.path.isfile(os.path.join(c, "retake", f)) for f in FILES):
             return c
     return None
@@ -52,12 +55,12 @@ class _LayerListView:
 _LOADED = None
 
 
-def load():
+def load(allow_system_tree=False):
     """-> (visual_compression module, shimmed PivotKVCache class, directory) or None when no reference tree is around"""
     global _LOADED
     if _LOADED is not None:
         return _LOADED
-    base = find()
+    base = find(allow_system_tree)
     if base is None:
         return None
     vc = _load(os.path.join(base, "retake", "visual_compression.py"), "retake_reference_visual_compression")
